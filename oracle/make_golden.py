@@ -1,0 +1,237 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference -- authoring container only.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Run as
+
+    python oracle/make_golden.py [--reference /root/reference] [--out tests/golden]
+
+It imports ``/root/reference/klhr.py`` and ``klhr_sinh.py`` untouched, with this
+directory's ``bsmodel.py`` shim ahead of the reference on ``sys.path`` (BridgeStan is not
+installable here), and swaps each sampler's public ``rng`` attribute (reference
+``mcmc.py:9-12``) for a TAPE generator that records every variate the sampler consumes.
+Per ``draw()`` (reference ``klhr.py:196-223`` / ``klhr_sinh.py:262-289``) the tape holds
+
+    theta0, rho, z_init, [init4], z_prop, u          inputs of the step
+    eta, zp, r, accept, theta1                       what the reference computed
+    grad_evals_draw                                  nfev1 + N * nfev2 (klhr.py:132,140)
+
+plus the adaptation state (``_mean``, ``_cov``, ``_eigvecs``, ``_eigvals``) after every
+window closure.  ``multivariate_normal`` is served as ``m + sqrt(diag S) * z`` (same law;
+NumPy's own routine routes z through an SVD permutation, SURVEY.md section 8a H3, which
+is why replay injects rho and never z).
+
+Nothing here is read on the GPU box: the fixtures are committed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+
+
+class TapeRNG:
+    """Generator look-alike recording the standard variates behind each call."""
+
+    def __init__(self, seed):
+        self._g = np.random.default_rng(seed)
+        self.log = []  # (kind, payload)
+
+    # reference call sites: klhr.py:91,129 ; klhr_sinh.py:191 ; klhr.py:180
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        z = self._g.standard_normal(size)
+        self.log.append(("normal", np.array(z, dtype=np.float64, copy=True)))
+        return loc + scale * z
+
+    # reference call site: klhr.py:188
+    def uniform(self, low=0.0, high=1.0, size=None):
+        u = self._g.random(size)
+        self.log.append(("uniform", np.array(u, dtype=np.float64, copy=True)))
+        return low + (high - low) * u
+
+    # reference call site: klhr.py:147 ; searchsorted(cumsum(p), u, 'right') is what NumPy does
+    def choice(self, a, p=None):
+        u = self._g.random()
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        j = int(np.searchsorted(cdf, u, side="right"))
+        self.log.append(("choice", np.array([u, j], dtype=np.float64)))
+        return j
+
+    # reference call site: klhr.py:152
+    def multivariate_normal(self, mean, cov):
+        z = self._g.standard_normal(np.size(mean))
+        x = np.asarray(mean, dtype=np.float64) + np.sqrt(np.diag(cov)) * z
+        self.log.append(("mvn", z.copy()))
+        return x
+
+
+def _tape_run(algo, M, family):
+    """Drive ``algo.draw()`` M times, capturing inputs/outputs of every step."""
+    rec = {k: [] for k in ("theta0", "rho", "z_init", "z_prop", "u", "eta", "zp", "r",
+                           "accept", "theta1", "grad_evals_draw", "ujdir")}
+    if family == "sinh":
+        rec["init4"] = []
+    closures = {"draw": [], "mean": [], "cov": [], "eigvecs": [], "eigvals": []}
+    cur = {}
+
+    orig_fit = algo.fit
+    orig_mh = algo._metropolis_step
+    logq = algo._logq if family == "gauss" else algo._log_q
+
+    def fit(rho):
+        cur["rho"] = np.array(rho, copy=True)
+        ge0 = algo.grad_evals
+        n0 = len(algo.rng.log)
+        eta = orig_fit(rho)
+        # variates consumed inside fit: 1 normal (stage-1 start) [+ normal(size=4) for sinh]
+        used = algo.rng.log[n0:]
+        cur["z_init"] = float(used[0][1])
+        if family == "sinh":
+            cur["init4"] = np.array(used[1][1], copy=True)
+        cur["eta"] = np.array(eta, copy=True)
+        cur["nfev"] = algo.grad_evals - ge0
+        return eta
+
+    def mh(eta, rho):
+        theta0 = np.array(algo.theta, copy=True)
+        n0 = len(algo.rng.log)
+        out = orig_mh(eta, rho)
+        used = algo.rng.log[n0:]
+        z = float(np.ravel(used[0][1])[0])
+        u = float(used[1][1])
+        if family == "gauss":
+            m, s = algo._unpack(eta)
+            zp = m + s * z
+        else:
+            zp = float(np.ravel(algo._T(np.array([z]), eta))[0])
+        thetap = zp * rho + theta0
+        r = algo.model.log_density(thetap) - algo.model.log_density(theta0)
+        with np.errstate(all="ignore"):
+            r = r + float(np.ravel(logq(0, eta))[0]) - float(np.ravel(logq(zp, eta))[0])
+        cur.update(theta0=theta0, z_prop=z, u=u, zp=zp, r=r,
+                   accept=bool(np.log(u) < np.minimum(0, r)),
+                   theta1=np.array(out, copy=True))
+        return out
+
+    algo.fit = fit
+    algo._metropolis_step = mh
+
+    for m in range(M):
+        n0 = len(algo.rng.log)
+        wa = algo._windowedadaptation
+        will_close = (wa._warmup >= wa._windowsize and wa._num_windows > 0
+                      and (algo._draw + 1) == wa._closures[wa._idx])
+        algo.draw()
+        first = algo.rng.log[n0]
+        rec["ujdir"].append(float(first[1][0]) if first[0] == "choice" else -1.0)
+        for k in rec:
+            if k in ("grad_evals_draw", "ujdir"):
+                continue
+            rec[k].append(cur[k])
+        rec["grad_evals_draw"].append(cur["nfev"])
+        assert cur["accept"] == (not np.array_equal(cur["theta0"], cur["theta1"])) or cur["zp"] == 0
+        if will_close:
+            closures["draw"].append(algo._draw)
+            closures["mean"].append(np.array(algo._mean, copy=True))
+            closures["cov"].append(np.array(algo._cov, copy=True))
+            closures["eigvecs"].append(np.array(algo._eigvecs, copy=True))
+            closures["eigvals"].append(np.array(algo._eigvals, copy=True))
+
+    out = {k: np.array(v) for k, v in rec.items()}
+    # theta1[m] == theta0[m+1]; keep only the last one to halve the fixture size
+    out["theta_last"] = out.pop("theta1")[-1]
+    for k, v in closures.items():
+        out["closure_" + k] = np.array(v)
+    out["acceptance_probability"] = np.array(float(np.ravel(algo.acceptance_probability)[0]))
+    out["grad_evals"] = np.array(int(algo.grad_evals))
+    return out
+
+
+CASES = [
+    # name, stan stem, data, family, draws, ctor kwargs, tighten-gtol
+    ("normal_d2_klhr", "normal", {"D": 2}, "gauss", 10_000, dict(seed=20261018), None),
+    ("illnormal_d100_klhr", "ill-normal", {"D": 100}, "gauss", 400, dict(seed=11, warmup=200), None),
+    ("illnormal_d100_klhr_tight", "ill-normal", {"D": 100}, "gauss", 200, dict(seed=12, warmup=100), 1e-12),
+    ("funnel_d2_klhr", "funnel", {"D": 1}, "gauss", 3_000, dict(seed=21), None),
+    ("funnel_d2_klhr_tight", "funnel", {"D": 1}, "gauss", 2_000, dict(seed=22), 1e-10),
+    ("funnel_d11_klhr_tight", "funnel", {"D": 10}, "gauss", 1_000, dict(seed=23), 1e-10),
+    ("funnel_d2_sinh", "funnel", {"D": 1}, "sinh", 2_000, dict(seed=31, overrelaxed=False), None),
+    ("funnel_d2_sinh_tight", "funnel", {"D": 1}, "sinh", 1_500, dict(seed=32, overrelaxed=False), 1e-9),
+    ("corrnormal_n50_klhr", "corr-normal", {"N": 50, "rho": 0.9}, "gauss", 400, dict(seed=41, warmup=200), None),
+    ("ar1_n100_klhr", "ar1", {"N": 100}, "gauss", 400, dict(seed=51, warmup=200), None),
+    ("ark_t200_klhr_tight", "arK", "arK.json", "gauss", 1_000, dict(seed=61), 1e-10),
+    ("ark_t200_sinh", "arK", "arK.json", "sinh", 500, dict(seed=62, overrelaxed=False), None),
+    ("rosenbrock_d4_klhr_tight", "rosenbrock", {"D": 2}, "gauss", 2_000, dict(seed=71), 1e-10),
+    ("rosenbrock_d4_sinh", "rosenbrock", {"D": 2}, "sinh", 1_000, dict(seed=72, overrelaxed=False), None),
+    ("normal_d2_klhr_method2", "normal", {"D": 2}, "gauss", 1_500,
+     dict(seed=81, eigen_method_one=False), None),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--out", default=str(HERE.parent / "tests" / "golden"))
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+
+    ref = Path(args.reference)
+    sys.path.insert(0, str(ref))
+    sys.path.insert(0, str(HERE))  # bare ``bsmodel`` -> the shim, ahead of the reference's
+
+    import functools
+    import bsmodel as shim
+    import klhr as ref_klhr
+    import klhr_sinh as ref_sinh
+    import scipy.optimize
+
+    out_dir = Path(args.out)
+    out_dir.mkdir(parents=True, exist_ok=True)
+
+    for name, stem, data, family, M, kw, gtol in CASES:
+        if args.only and args.only not in name:
+            continue
+        if isinstance(data, str):
+            data = json.loads((ref / "stan" / data).read_text())
+        model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
+        mod = ref_klhr if family == "gauss" else ref_sinh
+        # "tight" tapes: same reference code, SciPy asked for a smaller gtol by rebinding
+        # the module-level name the reference calls (klhr.py:5); sinh passes its own gtol
+        # through options (klhr_sinh.py:199) so it is overridden there.
+        if gtol is not None:
+            def tight(fun, x0, gtol=gtol, **k):
+                opts = dict(k.pop("options", None) or {})
+                opts["gtol"] = gtol
+                return scipy.optimize.minimize(fun, x0, options=opts, **k)
+            mod.minimize = tight
+        else:
+            mod.minimize = scipy.optimize.minimize
+        cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
+        seed = kw.pop("seed")
+        kw = dict(kw)
+        # construct with a plain seed (the ctor draws the start point), then tape
+        algo = cls(model, seed=seed, **kw)
+        algo.rng = TapeRNG(seed + 1000)
+        tape = _tape_run(algo, M, family)
+        tape["x_nodes"] = np.array(algo.x)
+        tape["w_nodes"] = np.array(algo.w)
+        meta = dict(case=name, model=stem, family=family, draws=M, ctor=dict(kw, seed=seed),
+                    gtol=gtol, numpy=np.__version__, scipy=scipy.__version__,
+                    tol=float(algo._tol), scale_clip=float(algo._scale_clip),
+                    initscale=float(algo._initscale), J=int(algo.J),
+                    eigen_method_one=bool(algo._eigen_method_one),
+                    closures=list(algo._windowedadaptation._closures))
+        dd = {k: v for k, v in data.items()}
+        tape["meta_json"] = np.array(json.dumps(meta))
+        tape["data_json"] = np.array(json.dumps(dd))
+        np.savez_compressed(out_dir / f"{name}.npz", **tape)
+        acc = float(tape["acceptance_probability"])
+        print(f"{name:32s} draws={M:6d} acc={acc:.3f} grad_evals/draw={int(tape['grad_evals']) / M:.1f}")
+
+
+if __name__ == "__main__":
+    main()

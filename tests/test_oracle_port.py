@@ -1,0 +1,41 @@
+"""The single-chain port (oracle/ref_port.py) must reproduce tapes of the UNMODIFIED
+reference bit for bit -- this is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle.bsmodel import BSModel
+from oracle.ref_port import replay_port
+
+CASES = [("normal_d2_klhr", 1100), ("normal_d2_klhr_method2", 400), ("illnormal_d100_klhr", 220),
+         ("funnel_d2_klhr", 200), ("funnel_d2_sinh", 60), ("corrnormal_n50_klhr", 210),
+         ("ar1_n100_klhr", 60), ("ark_t200_sinh", 40), ("rosenbrock_d4_sinh", 40)]
+
+
+@pytest.mark.parametrize("name,n", CASES)
+def test_port_is_bit_exact_on_reference_tape(tapes, name, n):
+    t, meta, data = tapes(name)
+    model = BSModel(stan_file=meta["model"] + ".stan", data=data)
+    kw = {k: v for k, v in meta["ctor"].items() if k != "seed"}
+    out = replay_port(t, model, meta["family"], n=n, **kw)
+    assert np.array_equal(out["eta"], t["eta"][:n])
+    assert np.array_equal(out["zp"], t["zp"][:n])
+    assert np.array_equal(out["r"], t["r"][:n], equal_nan=True)
+    assert np.array_equal(out["accept"], t["accept"][:n])
+    assert np.array_equal(out["theta"][:-1], t["theta0"][1:n])
+    s = out["sampler"]
+    k = int((t["closure_draw"] <= n).sum())
+    if k:   # adaptation state after the last closure inside the replayed range
+        assert np.array_equal(s.dir_mean, t["closure_mean"][k - 1])
+        assert np.array_equal(s.dir_cov, t["closure_cov"][k - 1])
+        assert np.array_equal(s.eigvecs, t["closure_eigvecs"][k - 1])
+        assert np.array_equal(s.eigvals, t["closure_eigvals"][k - 1])
+
+
+def test_quadrature_table(tapes):
+    # values after the reference's normalisation, klhr.py:46-49
+    from oracle.ref_port import gauss_hermite_probabilists
+    x, w = gauss_hermite_probabilists(8)
+    t, _, _ = tapes("normal_d2_klhr")
+    assert np.array_equal(x, t["x_nodes"]) and np.array_equal(w, t["w_nodes"])
+    assert np.isclose(w.sum(), 1) and np.isclose((w * x ** 2).sum(), 1) and np.isclose((w * x ** 4).sum(), 3)
+    assert np.allclose(np.abs(x[4:]), [0.5390798113513752, 1.6365190424351082, 2.802485861287542, 4.1445471861258945])
