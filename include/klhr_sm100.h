@@ -1,0 +1,159 @@
+/* libklhr_sm100.so -- C ABI of the B200-native KL Hit-and-Run step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference reaches native
+ * code through BridgeStan's C ABI, once per log-density evaluation (reference
+ * bsmodel.py:18,27 -> bridgestan ctypes -> bs_log_density[_gradient]); here one call
+ * advances EVERY chain by whole draws.  Each entry point names the reference interface it
+ * replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer inside the descriptor structs and every `*_dev` argument is a DEVICE
+ *     pointer (torch `tensor.data_ptr()`); the library never allocates persistent state;
+ *   - `dtype` selects the arithmetic type of all real buffers: KLHR_F64 or KLHR_F32;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default);
+ *   - return value: 0 ok, <0 invalid argument (see klhr_last_error), >0 a cudaError_t;
+ *   - no exceptions cross the ABI; the last-error string is thread-local.
+ */
+#ifndef KLHR_SM100_H_
+#define KLHR_SM100_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLHR_ABI_VERSION 1
+
+enum { KLHR_F64 = 0, KLHR_F32 = 1 };
+enum { KLHR_FAMILY_GAUSS = 0, KLHR_FAMILY_SINH = 1 };
+
+/* Stan programs of the reference with a hand-written device implementation
+ * (reference stan/<name>.stan). */
+enum {
+    KLHR_MODEL_NORMAL = 0,      /* stan/normal.stan       */
+    KLHR_MODEL_ILL_NORMAL = 1,  /* stan/ill-normal.stan   data0 = inv_s2[D]                       */
+    KLHR_MODEL_FUNNEL = 2,      /* stan/funnel.stan       i0 = D (number of alpha); dim = D + 1   */
+    KLHR_MODEL_CORR_NORMAL = 3, /* stan/corr-normal.stan  data0 = dense precision P[D*D]          */
+    KLHR_MODEL_AR1 = 4,         /* stan/ar1.stan          s0 = alpha, s1 = 1/beta^2               */
+    KLHR_MODEL_ARK = 5,         /* stan/arK.stan          i0 = K, i1 = T-K, data0 = [G|c|yy]      */
+    KLHR_MODEL_ROSENBROCK = 6,  /* stan/rosenbrock.stan   i0 = D; dim = 2 D                       */
+    KLHR_MODEL_COUNT = 7
+};
+
+/* Target density descriptor (replaces a bridgestan.StanModel handle, bsmodel.py:10-13). */
+typedef struct klhr_model {
+    int32_t id;          /* KLHR_MODEL_*                               */
+    int32_t dim;         /* number of unconstrained parameters         */
+    int32_t i0, i1;      /* model integers, see enum                   */
+    double s0, s1;       /* model scalars, see enum                    */
+    const void* data0;   /* device buffer of `dtype` reals, see enum   */
+    const void* data1;   /* reserved                                   */
+} klhr_model_t;
+
+#define KLHR_MAX_NODES 32
+
+/* Line-fit configuration: the reference's constructor arguments that reach the fit
+ * (klhr.py:16-49 / klhr_sinh.py:15-47) plus the fixed iteration budget that replaces
+ * scipy.optimize.minimize (klhr.py:127-139). */
+typedef struct klhr_fit {
+    int32_t family;              /* KLHR_FAMILY_*                                          */
+    int32_t n_nodes;             /* N, Gauss-Hermite nodes (<= KLHR_MAX_NODES)            */
+    int32_t n1, n2, nb;          /* stage-1 iterations, stage-2 Newton steps, halvings    */
+    int32_t reserved;
+    double initscale;            /* klhr.py:24                                            */
+    double tol;                  /* klhr.py:28 / klhr_sinh.py:26                          */
+    double scale_clip;           /* klhr.py:30 / klhr_sinh.py:28                          */
+    double gtol1, gtol2;         /* convergence thresholds of the two stages             */
+    double step_cap, c1, basin;  /* Newton step cap, Armijo constant, full-step basin     */
+    double x[KLHR_MAX_NODES];    /* nodes  hermgauss(N).x * sqrt(2)   (klhr.py:46-48)      */
+    double w[KLHR_MAX_NODES];    /* weights hermgauss(N).w / sqrt(pi) (klhr.py:49)         */
+} klhr_fit_t;
+
+/* Direction law of the step (KLHR._random_direction, klhr.py:143-153):
+ * rho = x / ||x + tol||, x ~ N(mean_j, diag(sd^2)), column j drawn with cumulative
+ * probabilities cdf[0..n_cols-1] (eigen_method_one) or n_cols == 1 (method two: the host
+ * pre-combines the eigenvectors).  A NULL `mean_cols` means a zero mean. */
+typedef struct klhr_direction {
+    const void* mean_cols;       /* [n_cols][D] reals or NULL                              */
+    const void* sd;              /* [D] reals, sqrt(_cov); NULL = ones                     */
+    const void* cdf;             /* [n_cols] reals, last entry 1; NULL when n_cols <= 1    */
+    int32_t n_cols;
+    int32_t reserved;
+} klhr_direction_t;
+
+/* Per-draw trace buffers, all optional (NULL = not written).  Layout [step][chain][..]. */
+typedef struct klhr_trace {
+    void* eta;        /* [S][B][2|4]  fitted line parameters (KLHR.fit return value)      */
+    void* zp;         /* [S][B]       proposal along the line                              */
+    void* r;          /* [S][B]       log MH ratio (klhr.py:183-186)                       */
+    int32_t* accept;  /* [S][B]                                                            */
+    int32_t* evals;   /* [S][B]       line evaluations (grad_evals increment)              */
+    void* rho;        /* [S][B][D]    direction used                                       */
+    void* z_init;     /* [S][B]       variates used (free-running mode only)               */
+    void* z_prop;     /* [S][B]                                                            */
+    void* u;          /* [S][B]                                                            */
+    void* init4;      /* [S][B][4]    sinh family only (entries 2,3 used)                  */
+} klhr_trace_t;
+
+/* Accumulators of a free-running launch, all optional. */
+typedef struct klhr_accum {
+    const void* shift;           /* [D] reals subtracted before accumulation (or NULL)     */
+    double* pooled_s1;           /* [D]  += sum over chains and draws of (theta - shift)   */
+    double* pooled_s2;           /* [D]  += sum of (theta - shift)^2                       */
+    double* chain_s1;            /* [B][D] += per-chain sum of (theta - shift)             */
+    double* chain_s2;            /* [B][D] += per-chain sum of squares                     */
+    long long* accept_count;     /* [B]  += accepted draws (acceptance_probability)        */
+    unsigned long long* evals_total; /* [1] += line evaluations (grad_evals)               */
+    void* draws;                 /* [S/thin][B][D] thinned draws (MCMCBase.sample rows)    */
+    int32_t thin;                /* write every `thin`-th draw (>= 1)                      */
+    int32_t skip_accum_last;     /* 1: the last draw of the launch is a window closure and
+                                    is not accumulated (klhr.py:202-221)                   */
+} klhr_accum_t;
+
+int klhr_abi_version(void);
+
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+size_t klhr_last_error(char* buf, size_t len);
+
+/* Batched BSModel.log_density / log_density_gradient (bsmodel.py:15-30):
+ * theta [B][D] -> lp [B], grad [B][D] (grad may be NULL).  Non-finite => lp = -inf,
+ * grad = 0, never an error. */
+int klhr_model_eval(const klhr_model_t* model, int dtype, const void* theta_dev, void* lp_dev,
+                    void* grad_dev, int64_t n_chains, void* stream);
+
+/* One KLHR.draw() / KLHRSINH.draw() for every chain with HOST-INJECTED variates
+ * (replay mode): theta [B][D] is advanced in place using rho [B][D], z_init [B],
+ * init4 [B][4] (sinh; may be NULL for gauss), z_prop [B], u [B].
+ * Replaces klhr.py:196-201 (direction excluded) for B chains at once. */
+int klhr_step_replay(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, void* theta_dev,
+                     const void* rho_dev, const void* z_init_dev, const void* init4_dev,
+                     const void* z_prop_dev, const void* u_dev, const klhr_trace_t* trace,
+                     int64_t n_chains, void* stream);
+
+/* n_steps full draws for every chain with the in-kernel Philox4x32-10 streams
+ * (free-running mode).  The variates of chain c at draw t depend only on
+ * (seed, chain_offset + c, draw_offset + t), so results do not depend on how chains are
+ * sharded over GPUs or how draws are split over launches.
+ * Replaces the loop MCMCBase.sample (mcmc.py:31-37) -> KLHR.draw (klhr.py:196-223). */
+int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direction_t* dir, int dtype,
+             void* theta_dev, int64_t n_chains, int64_t chain_offset, int64_t draw_offset,
+             int32_t n_steps, uint64_t seed, const klhr_accum_t* accum, const klhr_trace_t* trace,
+             void* stream);
+
+/* Pooled second-moment accumulation for the adaptation PCA (replaces the per-sample CCIPCA
+ * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,
+ * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype. */
+int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_dev, double* outer_dev,
+                          double* s1_dev, int64_t n_chains, int32_t dim, void* stream);
+
+/* Occupancy query used by bench.py: threads per CTA and dynamic shared bytes the step
+ * kernel would be launched with for this problem; returns resident CTAs per SM (<=0 error). */
+int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running,
+                     int accumulate, int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* regs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLHR_SM100_H_ */

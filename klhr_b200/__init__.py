@@ -1,0 +1,19 @@
+"""klhr_b200 -- B200-native KL Hit-and-Run (the hot path of roualdes/klhr).
+
+Public surface mirrors the reference: ``BSModel`` (reference bsmodel.py), ``KLHR``
+(klhr.py), ``KLHRSINH`` (klhr_sinh.py).  Everything numeric runs in hand-written sm_100a
+CUDA kernels behind the C ABI of ``libklhr_sm100.so`` (include/klhr_sm100.h); there is no
+CPU fallback.
+"""
+from .bsmodel import BSModel
+from .engine import FitConfig, Direction, Trace, step_replay, run, outer_accumulate, launch_info, gauss_hermite
+
+__all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "outer_accumulate",
+           "launch_info", "gauss_hermite"]
+
+try:  # samplers (import kept soft only so that partial checkouts still expose the engine)
+    from .klhr import KLHR
+    from .klhr_sinh import KLHRSINH
+    __all__ += ["KLHR", "KLHRSINH"]
+except ImportError:  # pragma: no cover
+    pass

@@ -1,0 +1,288 @@
+// klhr_b200 -- extern "C" entry points of libklhr_sm100.so (include/klhr_sm100.h).
+// Validation, error strings and dispatch only; the kernels are in klhr_step.cuh and the
+// per-model translation units.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+
+#include "klhr_step.cuh"
+
+namespace klhr {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static int cuda_fail(int e, const char* where) {
+    if (e > 0) {
+        g_last_error = std::string(where) + ": " + cudaGetErrorString((cudaError_t)e);
+    } else if (e == -20) {
+        g_last_error = std::string(where) + ": dimension too large for the shared-memory staged step";
+    }
+    return e;
+}
+
+static int check_model(const klhr_model_t* m, ModelParams& mp) {
+    if (!m) return fail(-1, "model is NULL");
+    if (m->id < 0 || m->id >= KLHR_MODEL_COUNT)
+        return fail(-2, "unknown model id: no device implementation (there is no CPU fallback)");
+    if (m->dim <= 0) return fail(-3, "model dim must be positive");
+    mp.id = m->id; mp.D = m->dim; mp.i0 = m->i0; mp.i1 = m->i1;
+    mp.s0 = m->s0; mp.s1 = m->s1; mp.p0 = m->data0; mp.p1 = m->data1;
+    switch (m->id) {
+        case KLHR_MODEL_ILL_NORMAL:
+            if (!m->data0) return fail(-4, "ill-normal needs data0 = inv_s2[D]");
+            break;
+        case KLHR_MODEL_CORR_NORMAL:
+            if (!m->data0) return fail(-4, "corr-normal needs data0 = P[D*D]");
+            break;
+        case KLHR_MODEL_FUNNEL:
+            if (m->i0 != m->dim - 1) return fail(-5, "funnel: dim must equal i0 + 1");
+            break;
+        case KLHR_MODEL_ARK:
+            if (!m->data0 || m->i0 < 0 || m->dim != m->i0 + 2 || m->i1 <= 0)
+                return fail(-5, "arK: need data0 = [G|c|yy], dim = K + 2, i1 = T - K > 0");
+            break;
+        case KLHR_MODEL_ROSENBROCK:
+            if (m->dim != 2 * m->i0) return fail(-5, "rosenbrock: dim must equal 2 * i0");
+            break;
+        case KLHR_MODEL_AR1:
+            if (!(m->s1 > 0)) return fail(-5, "ar1: s1 = 1/beta^2 must be positive");
+            break;
+        default: break;
+    }
+    return 0;
+}
+
+static int check_fit(const klhr_fit_t* f, FitParams& fp) {
+    if (!f) return fail(-1, "fit is NULL");
+    if (f->family != KLHR_FAMILY_GAUSS && f->family != KLHR_FAMILY_SINH) return fail(-6, "unknown family");
+    if (f->n_nodes < 1 || f->n_nodes > KLHR_MAX_NODES) return fail(-7, "n_nodes out of range");
+    if (f->n1 < 0 || f->n2 < 0 || f->nb < 1) return fail(-8, "iteration budgets out of range");
+    fp.family = f->family; fp.N = f->n_nodes; fp.n1 = f->n1; fp.n2 = f->n2; fp.nb = f->nb;
+    fp.initscale = f->initscale; fp.tol = f->tol; fp.scale_clip = f->scale_clip;
+    fp.gtol1 = f->gtol1; fp.gtol2 = f->gtol2; fp.step_cap = f->step_cap; fp.c1 = f->c1; fp.basin = f->basin;
+    for (int i = 0; i < kMaxNodes; ++i) {
+        fp.x[i] = i < f->n_nodes ? f->x[i] : 0.0;
+        fp.w[i] = i < f->n_nodes ? f->w[i] : 0.0;
+        fp.cx[i] = std::asinh(fp.x[i]);
+    }
+    return 0;
+}
+
+static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, bool accum, cudaStream_t st,
+                         LaunchInfo* info) {
+    switch (a.mp.id) {
+        case KLHR_MODEL_NORMAL: return launch_step_normal(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_ILL_NORMAL: return launch_step_ill_normal(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_FUNNEL: return launch_step_funnel(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_CORR_NORMAL: return launch_step_corr_normal(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_AR1: return launch_step_ar1(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_ARK: return launch_step_ark(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_ROSENBROCK: return launch_step_rosenbrock(a, dtype, family, replay, accum, st, info);
+    }
+    return fail(-2, "unknown model id");
+}
+
+// ------------------------------------------------------------------ pooled outer products
+// outer[i][j] += sum_c (theta_ci - shift_i)(theta_cj - shift_j): a tall-skinny SYRK.  Each CTA
+// owns a 32x32 tile of the output and a slice of the chains; fp64 accumulation.
+template <typename R>
+__global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta, const R* __restrict__ shift,
+                                                    double* __restrict__ outer, double* __restrict__ s1,
+                                                    long long B, int D, int chains_per_cta) {
+    __shared__ double ta[32][33], tb[32][33];
+    const int ti = blockIdx.x * 32, tj = blockIdx.y * 32;
+    if (tj < ti) return;                                 // upper triangle only; mirrored below
+    const long long c_begin = (long long)blockIdx.z * chains_per_cta;
+    const long long c_end = c_begin + chains_per_cta < B ? c_begin + chains_per_cta : B;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    double acc[4] = {0, 0, 0, 0};
+    double colsum = 0;
+    for (long long c0 = c_begin; c0 < c_end; c0 += 32) {
+        // load 32 chains x 32 dims for both tiles
+        for (int r = ty; r < 32; r += 8) {
+            const long long c = c0 + r;
+            const int ia = ti + tx, ib = tj + tx;
+            double va = 0, vb = 0;
+            if (c < c_end) {
+                if (ia < D) va = (double)theta[c * D + ia] - (shift ? (double)shift[ia] : 0.0);
+                if (ib < D) vb = (double)theta[c * D + ib] - (shift ? (double)shift[ib] : 0.0);
+            }
+            ta[r][tx] = va;
+            tb[r][tx] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const double b = tb[k][tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += ta[k][ty + 8 * q] * b;
+        }
+        if (s1 && blockIdx.y == blockIdx.x && ty == 0)
+            for (int k = 0; k < 32; ++k) colsum += ta[k][tx];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = ti + ty + 8 * q, j = tj + tx;
+        if (i < D && j < D) {
+            atomicAdd(outer + (size_t)i * D + j, acc[q]);
+            if (ti != tj) atomicAdd(outer + (size_t)j * D + i, acc[q]);
+        }
+    }
+    if (s1 && blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) atomicAdd(s1 + ti + tx, colsum);
+}
+
+}  // namespace klhr
+
+using namespace klhr;
+
+extern "C" {
+
+int klhr_abi_version(void) { return KLHR_ABI_VERSION; }
+
+size_t klhr_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return g_last_error.size();
+    const size_t n = g_last_error.size() < len - 1 ? g_last_error.size() : len - 1;
+    std::memcpy(buf, g_last_error.data(), n);
+    buf[n] = 0;
+    return n;
+}
+
+int klhr_model_eval(const klhr_model_t* model, int dtype, const void* theta_dev, void* lp_dev, void* grad_dev,
+                    int64_t n_chains, void* stream) {
+    ModelParams mp;
+    if (int e = check_model(model, mp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (!theta_dev || !lp_dev) return fail(-1, "theta and lp must not be NULL");
+    if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = -2;
+    switch (mp.id) {
+        case KLHR_MODEL_NORMAL: e = launch_eval_normal(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_ILL_NORMAL: e = launch_eval_ill_normal(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_FUNNEL: e = launch_eval_funnel(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_CORR_NORMAL: e = launch_eval_corr_normal(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_AR1: e = launch_eval_ar1(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_ARK: e = launch_eval_ark(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_ROSENBROCK: e = launch_eval_rosenbrock(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+    }
+    return cuda_fail(e, "klhr_model_eval");
+}
+
+int klhr_step_replay(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, void* theta_dev,
+                     const void* rho_dev, const void* z_init_dev, const void* init4_dev, const void* z_prop_dev,
+                     const void* u_dev, const klhr_trace_t* trace, int64_t n_chains, void* stream) {
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_fit(fit, a.fp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (!theta_dev || !rho_dev || !z_init_dev || !z_prop_dev || !u_dev)
+        return fail(-1, "theta, rho, z_init, z_prop, u must not be NULL");
+    if (fit->family == KLHR_FAMILY_SINH && !init4_dev) return fail(-1, "sinh family needs init4");
+    if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    a.theta = theta_dev; a.B = n_chains;
+    a.rho = rho_dev; a.z_init = z_init_dev; a.init4 = init4_dev; a.z_prop = z_prop_dev; a.u = u_dev;
+    a.n_steps = 1;
+    a.acc.thin = 1;
+    if (trace) a.tr = *trace;
+    a.tr.z_init = a.tr.z_prop = a.tr.u = a.tr.init4 = nullptr;   // inputs in this mode
+    return cuda_fail(dispatch_step(a, dtype, fit->family, true, false, (cudaStream_t)stream, nullptr),
+                     "klhr_step_replay");
+}
+
+static int fill_run(StepArgs& a, const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direction_t* dir,
+                    int dtype, int64_t n_chains, const klhr_accum_t* accum, const klhr_trace_t* trace, bool& use_acc) {
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_fit(fit, a.fp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    if (dir) {
+        a.dir = *dir;
+        if (a.dir.mean_cols && a.dir.n_cols < 1) return fail(-11, "direction: n_cols must be >= 1 with mean_cols");
+        if (a.dir.mean_cols && a.dir.n_cols > 1 && !a.dir.cdf) return fail(-11, "direction: cdf needed when n_cols > 1");
+        if (!a.dir.mean_cols) a.dir.n_cols = 0;
+    }
+    a.acc.thin = 1;
+    use_acc = false;
+    if (accum) {
+        a.acc = *accum;
+        if (a.acc.thin < 1) a.acc.thin = 1;
+        if ((a.acc.pooled_s1 == nullptr) != (a.acc.pooled_s2 == nullptr))
+            return fail(-12, "pooled_s1 and pooled_s2 must be given together");
+        use_acc = a.acc.pooled_s1 || a.acc.chain_s1 || a.acc.chain_s2;
+    }
+    if (trace) {
+        a.tr = *trace;
+        if (a.tr.z_init && (!a.tr.z_prop || !a.tr.u)) return fail(-13, "trace: z_init, z_prop, u go together");
+    }
+    a.B = n_chains;
+    return 0;
+}
+
+int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direction_t* dir, int dtype,
+             void* theta_dev, int64_t n_chains, int64_t chain_offset, int64_t draw_offset, int32_t n_steps,
+             uint64_t seed, const klhr_accum_t* accum, const klhr_trace_t* trace, void* stream) {
+    StepArgs a;
+    bool use_acc;
+    if (int e = fill_run(a, model, fit, dir, dtype, n_chains, accum, trace, use_acc)) return e;
+    if (!theta_dev) return fail(-1, "theta must not be NULL");
+    if (n_steps < 0 || chain_offset < 0 || draw_offset < 0) return fail(-10, "negative count or offset");
+    if (n_steps == 0) return 0;
+    a.theta = theta_dev;
+    a.chain_offset = chain_offset; a.draw_offset = draw_offset; a.n_steps = n_steps; a.seed = seed;
+    return cuda_fail(dispatch_step(a, dtype, fit->family, false, use_acc, (cudaStream_t)stream, nullptr), "klhr_run");
+}
+
+int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running, int accumulate,
+                     int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* regs) {
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_fit(fit, a.fp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    a.acc.thin = 1;
+    LaunchInfo li;
+    const int e = dispatch_step(a, dtype, fit->family, !free_running, accumulate != 0, nullptr, &li);
+    if (e) return cuda_fail(e, "klhr_launch_info") > 0 ? -30 : e;
+    if (threads_per_cta) *threads_per_cta = li.threads;
+    if (smem_bytes) *smem_bytes = li.smem;
+    if (regs) *regs = li.regs;
+    return li.ctas_per_sm;
+}
+
+int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_dev, double* outer_dev, double* s1_dev,
+                          int64_t n_chains, int32_t dim, void* stream) {
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (!theta_dev || !outer_dev) return fail(-1, "theta and outer must not be NULL");
+    if (n_chains < 0 || dim <= 0) return fail(-10, "bad sizes");
+    if (n_chains == 0) return 0;
+    const int tiles = (dim + 31) / 32;
+    // enough chain slices to fill the machine: ~148 SMs * 4 CTAs over the upper-triangle tiles
+    const int tri = tiles * (tiles + 1) / 2;
+    long long slices = (592 + tri - 1) / tri;
+    const long long max_slices = (n_chains + 255) / 256;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    long long per = (n_chains + slices - 1) / slices;
+    per = ((per + 31) / 32) * 32;
+    slices = (n_chains + per - 1) / per;
+    dim3 grid(tiles, tiles, (unsigned)slices);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KLHR_F64)
+        outer_kernel<double><<<grid, 256, 0, st>>>((const double*)theta_dev, (const double*)shift_dev, outer_dev,
+                                                   s1_dev, n_chains, dim, (int)per);
+    else
+        outer_kernel<float><<<grid, 256, 0, st>>>((const float*)theta_dev, (const float*)shift_dev, outer_dev,
+                                                  s1_dev, n_chains, dim, (int)per);
+    return cuda_fail((int)cudaGetLastError(), "klhr_outer_accumulate");
+}
+
+}  // extern "C"

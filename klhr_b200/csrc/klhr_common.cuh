@@ -1,0 +1,143 @@
+// klhr_b200 -- device-side building blocks shared by all kernels (sm_100a).
+//
+// Execution shape: an OCTET (8 consecutive lanes of a warp) owns one chain.  The 8 lanes
+// are the 8 Gauss-Hermite nodes during the KL fit (reference klhr.py:110-117 loops over
+// them serially), the 8 back-tracking candidates during the 1-D mode search, and 8
+// interleaved slices of the D-vector during direction / line-setup / update.  Reductions
+// are 3-level xor-shuffles confined to the octet.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace klhr {
+
+constexpr int kOct = 8;                 // lanes per chain
+constexpr int kMaxNodes = 32;           // quadrature nodes supported (reference default N = 8)
+
+__device__ __forceinline__ unsigned oct_mask() {
+    return 0xFFu << ((threadIdx.x & 31u) & 24u);
+}
+
+template <typename R>
+__device__ __forceinline__ R oct_sum(R v, unsigned m) {
+    v += __shfl_xor_sync(m, v, 1);
+    v += __shfl_xor_sync(m, v, 2);
+    v += __shfl_xor_sync(m, v, 4);
+    return v;
+}
+
+// broadcast from lane `src` (0..7) of this octet
+template <typename R>
+__device__ __forceinline__ R oct_bcast(R v, int src, unsigned m) {
+    return __shfl_sync(m, v, src, kOct);
+}
+
+// ------------------------------------------------------------------ Real traits
+template <typename R> struct Num;
+template <> struct Num<double> {
+    static constexpr double eps = 2.220446049250313e-16;
+    __device__ static __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <> struct Num<float> {
+    static constexpr float eps = 1.1920929e-07f;
+    __device__ static __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+
+__device__ __forceinline__ double r_exp(double x) { return exp(x); }
+__device__ __forceinline__ float r_exp(float x) { return expf(x); }
+__device__ __forceinline__ double r_log(double x) { return log(x); }
+__device__ __forceinline__ float r_log(float x) { return logf(x); }
+__device__ __forceinline__ double r_log1p(double x) { return log1p(x); }
+__device__ __forceinline__ float r_log1p(float x) { return log1pf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double r_sinh(double x) { return sinh(x); }
+__device__ __forceinline__ float r_sinh(float x) { return sinhf(x); }
+__device__ __forceinline__ double r_cosh(double x) { return cosh(x); }
+__device__ __forceinline__ float r_cosh(float x) { return coshf(x); }
+__device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ double r_asinh(double x) { return asinh(x); }
+__device__ __forceinline__ float r_asinh(float x) { return asinhf(x); }
+__device__ __forceinline__ bool r_finite(double x) { return isfinite(x); }
+__device__ __forceinline__ bool r_finite(float x) { return isfinite(x); }
+template <typename R> __device__ __forceinline__ R r_clamp(R v, R lo, R hi) { return v < lo ? lo : (v > hi ? hi : v); }
+template <typename R> __device__ __forceinline__ R r_max(R a, R b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------ line restriction value
+// (l(y) - l(0), l'(y), l''(y)); non-finite anywhere -> (-inf, 0, 0): the batched form of the
+// reference wrapper's "failure => -inf / zero gradient" (bsmodel.py:15-30).
+template <typename R> struct Jet { R l, l1, l2; };
+
+template <typename R>
+__device__ __forceinline__ Jet<R> jet_guard(R l, R l1, R l2) {
+    Jet<R> j;
+    const bool ok = r_finite(l) && r_finite(l1) && r_finite(l2);
+    j.l = ok ? l : -Num<R>::inf();
+    j.l1 = ok ? l1 : R(0);
+    j.l2 = ok ? l2 : R(0);
+    return j;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Counter-based generator (Salmon et al. 2011): zero bytes of RNG state per chain.
+// counter = (chain_lo, chain_hi, draw, slot), key = (seed_lo, seed_hi).
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    static constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __host__ __device__ static inline void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint64_t p0 = (uint64_t)M0 * c0;
+            const uint64_t p1 = (uint64_t)M1 * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+            const uint32_t n1 = (uint32_t)p1;
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+            const uint32_t n3 = (uint32_t)p0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += W0; k1 += W1;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// slots of one (chain, draw) stream
+constexpr uint32_t kSlotScalarA = 0;   // w0: direction-column uniform; w2,w3: z_init pair
+constexpr uint32_t kSlotProposal = 1;  // w0..w3: two 53-bit uniforms -> Box-Muller -> z_prop
+constexpr uint32_t kSlotAccept = 2;    // w0,w1: 53-bit accept uniform
+constexpr uint32_t kSlotInit4 = 3;     // w0..w3: two Box-Muller pairs -> init4[2], init4[3] (sinh)
+constexpr uint32_t kSlotDir = 8;       // + lane + 8*q : 4 direction normals per block
+
+// uniform in (0,1) from 32 bits: (x + 0.5) / 2^32
+__device__ __forceinline__ float u01_32(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1) from 53 of 64 bits
+__device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
+    const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Box-Muller, single precision, fast intrinsics: direction normals only need to be a valid
+// random direction law (any rho is a valid hit-and-run direction), not 1-ulp accurate.
+__device__ __forceinline__ void box_muller_f32(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u = u01_32(a);
+    const float v = u01_32(b);
+    const float rad = sqrtf(-2.0f * __logf(u));
+    float s, c;
+    __sincosf(6.283185307179586f * v, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+__device__ __forceinline__ void box_muller_f64(double u, double v, double& z0, double& z1) {
+    const double rad = sqrt(-2.0 * log(u));
+    double s, c;
+    sincospi(2.0 * v, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+}  // namespace klhr

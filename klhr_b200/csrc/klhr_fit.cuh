@@ -1,0 +1,419 @@
+// klhr_b200 -- the line fit (reference KLHR.fit klhr.py:126-141, KLHRSINH.fit
+// klhr_sinh.py:182-201) with scipy.optimize.minimize replaced by a fixed-budget damped
+// Newton iteration, and the Metropolis-Hastings pieces (klhr.py:155-158,175-190,
+// klhr_sinh.py:112-114,233-260).  Mirrors oracle/batched.py operation for operation.
+//
+// All functions are called by the 8 lanes of an octet together; every scalar they return
+// is uniform across the octet.  Lane n owns quadrature node n (n, n+8, .. for N > 8).
+#pragma once
+#include "klhr_common.cuh"
+
+namespace klhr {
+
+struct FitParams {
+    int family;            // KLHR_FAMILY_GAUSS | KLHR_FAMILY_SINH
+    int N;                 // quadrature nodes (<= kMaxNodes)
+    int n1, n2, nb;        // stage-1 iterations, stage-2 Newton steps, halvings per step
+    double initscale, tol, scale_clip;
+    double gtol1, gtol2, step_cap, c1, basin;
+    double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
+};
+
+template <typename R>
+struct FitResult {
+    R eta[4];
+    int evals;             // line evaluations executed (the reference's grad_evals, klhr.py:132,140)
+    bool converged;
+};
+
+// ------------------------------------------------------------------ stage 1: 1-D mode search
+template <typename R, typename Model>
+__device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitParams& fp, int lane,
+                            unsigned m, R& xi_out, R& tau0_out, int& nev) {
+    R xi = z_init * (R)fp.initscale;
+    R trust = 1;
+    bool done = false;
+    Jet<R> J = Model::eval(cf, xi);
+    nev = 1;
+    const R ks = (R)1 / (R)(1 << lane);
+    for (int it = 0; it < fp.n1; ++it) {
+        const bool concave = J.l2 < R(0);
+        const R sc = concave ? R(1) / r_sqrt(-J.l2) : R(1);
+        const bool conv = concave && (r_abs(J.l1) * sc <= (R)fp.gtol1);
+        done = done || conv || !r_finite(J.l);
+        if (done) break;
+        const R newton = concave ? -J.l1 / J.l2 : R(0);
+        const R step = concave ? r_clamp(newton, -R(8) * trust, R(8) * trust) : r_clamp(J.l1, -trust, trust);
+        const R cand = xi + step * ks;
+        const Jet<R> C = Model::eval(cf, cand);
+        nev += kOct;
+        // arg-max of C.l over the octet, first maximum on ties
+        R bv = C.l;
+        int bi = lane;
+#pragma unroll
+        for (int off = 1; off < kOct; off <<= 1) {
+            const R ov = __shfl_xor_sync(m, bv, off);
+            const int oi = __shfl_xor_sync(m, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const bool improve = bv > J.l;
+        const bool full = improve && bi == 0;
+        if (improve) {
+            xi = oct_bcast(cand, bi, m);
+            J.l = bv;
+            J.l1 = oct_bcast(C.l1, bi, m);
+            J.l2 = oct_bcast(C.l2, bi, m);
+        }
+        trust = full ? trust * R(2) : (improve ? trust : trust * R(1.0 / 256.0));
+        done = done || (!improve && (r_abs(step) * R(1.0 / 128.0) <= Num<R>::eps * (R(1) + r_abs(xi))));
+    }
+    xi_out = xi;
+    tau0_out = (J.l2 < R(0)) ? R(0.5) * r_log(-R(1) / J.l2) : R(0);
+}
+
+// ------------------------------------------------------------------ small dense algebra
+template <typename R, int n>
+struct KLState {
+    R f;
+    R g[n];
+    R H[n][n];          // full symmetric storage (n = 2 or 4)
+};
+
+// Solve (H) p = -g by Cholesky, entry by entry like oracle/batched.py:_chol_solve.
+template <typename R, int n>
+__device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R (&g)[n], R (&p)[n]) {
+    R L[n][n];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        R acc = H[j][j] + shift;
+#pragma unroll
+        for (int k = 0; k < j; ++k) acc = acc - L[j][k] * L[j][k];
+        ok = ok && (acc > R(0));
+        const R ljj = r_sqrt(acc > R(0) ? acc : R(1));
+        L[j][j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            R a2 = H[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) a2 = a2 - L[i][k] * L[j][k];
+            L[i][j] = a2 / ljj;
+        }
+    }
+    R y[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        R acc = -g[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = acc - L[i][k] * y[k];
+        y[i] = acc / L[i][i];
+    }
+#pragma unroll
+    for (int i = n - 1; i >= 0; --i) {
+        R acc = y[i];
+#pragma unroll
+        for (int k = i + 1; k < n; ++k) acc = acc - L[k][i] * p[k];
+        p[i] = acc / L[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) ok = ok && r_finite(p[i]);
+    return ok;
+}
+
+template <typename R, int n>
+__device__ __forceinline__ void newton_direction(const KLState<R, n>& S, const FitParams& fp, R (&p)[n]) {
+    R mu = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mu = r_max(mu, r_abs(S.H[i][i]));   // NaN-safe: comparisons drop NaN
+    bool mu_ok = true;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mu_ok = mu_ok && r_finite(S.H[i][i]);
+    if (!(mu_ok && mu > R(0))) mu = R(1);
+    // Levenberg shifts (x mu): 0, 1e-3, 1e-2, 1e-1, 1, 10, 100, 1e3, 1e4, 1e6 -- same list as
+    // oracle/batched.py:LM_SHIFTS; generated arithmetically to keep the table out of local memory
+    bool have = false;
+    R shift = R(0);
+    for (int k = 0; k < 10 && !have; ++k) {
+        R pk[n];
+        if (chol_solve<R, n>(S.H, shift * mu, S.g, pk)) {
+            have = true;
+#pragma unroll
+            for (int i = 0; i < n; ++i) p[i] = pk[i];
+        }
+        shift = k == 0 ? R(1e-3) : (k == 8 ? R(1e6) : shift * R(10));
+    }
+    if (!have) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) p[i] = -S.g[i];
+    }
+    R big = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        if (!r_finite(p[i])) p[i] = R(0);
+        big = r_max(big, r_abs(p[i]));
+    }
+    const R cap = (R)fp.step_cap;
+    const R scale = big > cap ? cap / big : R(1);
+#pragma unroll
+    for (int i = 0; i < n; ++i) p[i] = p[i] * scale;
+}
+
+// ------------------------------------------------------------------ KL objective, Gaussian family
+// reference klhr.py:106-120 in scaled coordinates (m/s, tau); Hessian from l''.
+template <typename R, typename Model>
+__device__ void kl_gauss(const typename Model::Coef& cf, const R (&eta)[2], const FitParams& fp, int lane,
+                         unsigned m, KLState<R, 2>& S) {
+    const R clip = (R)fp.scale_clip;
+    const R s = r_exp(r_clamp(eta[1], -clip, clip));
+    R S0 = 0, S1 = 0, S1x = 0, S2 = 0, S2x = 0, S2xx = 0;
+    for (int n = lane; n < fp.N; n += kOct) {
+        const R x = (R)fp.x[n], w = (R)fp.w[n];
+        const R y = s * x + eta[0];
+        const Jet<R> J = Model::eval(cf, y);
+        S0 += w * J.l;
+        const R w1 = w * J.l1;
+        S1 += w1;
+        S1x += w1 * x;
+        const R w2 = w * J.l2;
+        S2 += w2;
+        S2x += w2 * x;
+        S2xx += w2 * x * x;
+    }
+    S0 = oct_sum(S0, m); S1 = oct_sum(S1, m); S1x = oct_sum(S1x, m);
+    S2 = oct_sum(S2, m); S2x = oct_sum(S2x, m); S2xx = oct_sum(S2xx, m);
+    const R s2 = s * s;
+    S.f = -(S0 + eta[1]);
+    S.g[0] = -S1 * s;
+    S.g[1] = -(S1x * s + R(1));
+    S.H[0][0] = -S2 * s2;
+    S.H[0][1] = S.H[1][0] = -S2x * s2;
+    S.H[1][1] = -(S2xx * s2 + S1x * s);
+}
+
+// ------------------------------------------------------------------ sinh-arcsinh family
+template <typename R>
+struct SinhPar { R m, s, d, e; };
+
+template <typename R>
+__device__ __forceinline__ SinhPar<R> sinh_unpack(const R (&eta)[4], const FitParams& fp) {   // klhr_sinh.py:78-84
+    const R c = (R)fp.scale_clip, tol = (R)fp.tol;
+    SinhPar<R> q;
+    q.m = eta[0];
+    q.s = r_exp(r_clamp(eta[1], -c, c)) + tol;
+    q.d = r_exp(r_clamp(eta[2], -c, c)) + tol;
+    q.e = eta[3];
+    return q;
+}
+
+// reference klhr_sinh.py:163-176; gradients are _grad_T (:116-124) and _grad_log_abs_jac
+// (:146-156); second derivatives are those expressions differentiated once more.
+template <typename R, typename Model>
+__device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const FitParams& fp, int lane,
+                        unsigned m, KLState<R, 4>& S) {
+    const SinhPar<R> q = sinh_unpack<R>(eta, fp);
+    const R c = (R)fp.scale_clip;
+    const R invd = R(1) / q.d;
+    R f = 0, g1 = 0, g2 = 0, g3 = 0, g0 = 0;
+    R h00 = 0, h01 = 0, h02 = 0, h03 = 0, h11 = 0, h12 = 0, h13 = 0, h22 = 0, h23 = 0, h33 = 0;
+    for (int n = lane; n < fp.N; n += kOct) {
+        const R w = (R)fp.w[n];
+        const R a = ((R)fp.cx[n] + q.e) * invd;
+        const R ac = r_clamp(a, -c, c);
+        const R sh = r_sinh(ac), ch = r_cosh(ac), th = r_tanh(ac);
+        const R sech2 = R(1) - th * th;
+        const R T = q.m + q.s * sh;
+        const Jet<R> J = Model::eval(cf, T);
+        const R logJ = (eta[2] - eta[1]) - r_log(ch);
+        f += w * (logJ - J.l);
+        const R t1 = q.s * sh, t2 = -q.s * ch * a, t3 = q.s * ch * invd;          // grad T (t0 = 1)
+        const R L2 = R(1) + th * a, L3 = -th * invd;                              // grad log|J| (L0 = 0, L1 = -1)
+        g0 += w * (-J.l1);
+        g1 += w * (-R(1) - J.l1 * t1);
+        g2 += w * (L2 - J.l1 * t2);
+        g3 += w * (L3 - J.l1 * t3);
+        const R T11 = q.s * sh, T12 = -q.s * a * ch, T13 = q.s * ch * invd;
+        const R T22 = q.s * a * ch + q.s * a * a * sh;
+        const R T23 = -(q.s * invd) * (ch + a * sh);
+        const R T33 = q.s * sh * invd * invd;
+        const R L22 = -a * th - a * a * sech2;
+        const R L23 = (th + a * sech2) * invd;
+        const R L33 = -sech2 * invd * invd;
+        h00 += w * (-J.l2);
+        h01 += w * (-J.l2 * t1);
+        h02 += w * (-J.l2 * t2);
+        h03 += w * (-J.l2 * t3);
+        h11 += w * (-J.l2 * t1 * t1 - J.l1 * T11);
+        h12 += w * (-J.l2 * t1 * t2 - J.l1 * T12);
+        h13 += w * (-J.l2 * t1 * t3 - J.l1 * T13);
+        h22 += w * (L22 - J.l2 * t2 * t2 - J.l1 * T22);
+        h23 += w * (L23 - J.l2 * t2 * t3 - J.l1 * T23);
+        h33 += w * (L33 - J.l2 * t3 * t3 - J.l1 * T33);
+    }
+    S.f = oct_sum(f, m);
+    g0 = oct_sum(g0, m); g1 = oct_sum(g1, m); g2 = oct_sum(g2, m); g3 = oct_sum(g3, m);
+    h00 = oct_sum(h00, m); h01 = oct_sum(h01, m); h02 = oct_sum(h02, m); h03 = oct_sum(h03, m);
+    h11 = oct_sum(h11, m); h12 = oct_sum(h12, m); h13 = oct_sum(h13, m);
+    h22 = oct_sum(h22, m); h23 = oct_sum(h23, m); h33 = oct_sum(h33, m);
+    const R s = q.s;
+    S.g[0] = g0 * s; S.g[1] = g1; S.g[2] = g2; S.g[3] = g3;
+    S.H[0][0] = h00 * s * s;
+    S.H[0][1] = S.H[1][0] = h01 * s;
+    S.H[0][2] = S.H[2][0] = h02 * s;
+    S.H[0][3] = S.H[3][0] = h03 * s;
+    S.H[1][1] = h11; S.H[1][2] = S.H[2][1] = h12; S.H[1][3] = S.H[3][1] = h13;
+    S.H[2][2] = h22; S.H[2][3] = S.H[3][2] = h23; S.H[3][3] = h33;
+}
+
+template <typename R, typename Model, int n>
+__device__ __forceinline__ void kl_eval(const typename Model::Coef& cf, const R (&eta)[n], const FitParams& fp,
+                                        int lane, unsigned m, KLState<R, n>& S) {
+    if constexpr (n == 2) kl_gauss<R, Model>(cf, eta, fp, lane, m, S);
+    else kl_sinh<R, Model>(cf, eta, fp, lane, m, S);
+}
+
+template <typename R, int n>
+__device__ __forceinline__ R scale_of(const R (&eta)[n], const FitParams& fp) {
+    const R c = (R)fp.scale_clip;
+    const R s = r_exp(r_clamp(eta[1], -c, c));
+    return n == 4 ? s + (R)fp.tol : s;
+}
+
+// ------------------------------------------------------------------ stage 2: damped Newton on KL
+template <typename R, typename Model, int n>
+__device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
+                              unsigned m, int& nev, bool& converged) {
+    KLState<R, n> S;
+    kl_eval<R, Model, n>(cf, eta, fp, lane, m, S);
+    nev = 1;
+    bool conv = false;
+    for (int it = 0; it < fp.n2; ++it) {
+        R gmax = 0;
+        bool gnan = false;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            gmax = r_max(gmax, r_abs(S.g[i]));
+            gnan = gnan || (S.g[i] != S.g[i]);
+        }
+        if (!gnan && gmax <= (R)fp.gtol2) { conv = true; break; }
+        R p[n];
+        newton_direction<R, n>(S, fp, p);
+        R gp = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) gp += S.g[i] * p[i];
+        if (!r_finite(gp)) gp = 0;
+        const R s_cur = scale_of<R, n>(eta, fp);
+        const bool in_basin = !gnan && gmax <= (R)fp.basin;
+        R t = 1;
+        bool accepted = false;
+        for (int bt = 0; bt < fp.nb; ++bt) {
+            R trial[n];
+            trial[0] = eta[0] + t * p[0] * s_cur;
+#pragma unroll
+            for (int i = 1; i < n; ++i) trial[i] = eta[i] + t * p[i];
+            KLState<R, n> St;
+            kl_eval<R, Model, n>(cf, trial, fp, lane, m, St);
+            nev += 1;
+            const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S.f));
+            const bool ok = r_finite(St.f) &&
+                            ((St.f <= S.f + (R)fp.c1 * t * gp + slack) || !r_finite(S.f) || in_basin);
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) eta[i] = trial[i];
+                S = St;
+                accepted = true;
+                break;
+            }
+            t *= R(0.5);
+        }
+        if (!accepted) break;          // stalled: keep the current iterate
+    }
+    if (!conv) {
+        R gmax = 0;
+        bool gnan = false;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            gmax = r_max(gmax, r_abs(S.g[i]));
+            gnan = gnan || (S.g[i] != S.g[i]);
+        }
+        conv = !gnan && gmax <= (R)fp.gtol2;
+    }
+    converged = conv;
+}
+
+// ------------------------------------------------------------------ family densities / transport
+template <typename R>
+__device__ __forceinline__ R logq_gauss(R x, const R (&eta)[2], const FitParams& fp) {          // klhr.py:155-158
+    const R c = (R)fp.scale_clip;
+    const R s = r_exp(r_clamp(eta[1], -c, c));
+    const R z = (x - eta[0]) / s;
+    return -r_log(s) - R(0.5) * z * z;
+}
+
+template <typename R>
+__device__ __forceinline__ R transport_sinh(R z, const R (&eta)[4], const FitParams& fp) {       // klhr_sinh.py:112-114
+    const SinhPar<R> q = sinh_unpack<R>(eta, fp);
+    const R c = (R)fp.scale_clip;
+    return q.m + q.s * r_sinh(r_clamp((r_asinh(z) + q.e) / q.d, -c, c));
+}
+
+template <typename R>
+__device__ __forceinline__ R logq_sinh(R x, const R (&eta)[4], const FitParams& fp) {            // klhr_sinh.py:233-240
+    const SinhPar<R> q = sinh_unpack<R>(eta, fp);
+    const R c = (R)fp.scale_clip;
+    const R z = (x - q.m) / q.s;
+    const R b = r_clamp(q.d * r_asinh(z) - q.e, -c, c);
+    const R ti = r_sinh(b);
+    return -R(0.5) * ti * ti + r_log(r_cosh(b)) + eta[2] - eta[1] - R(0.5) * r_log1p(z * z);
+}
+
+// ------------------------------------------------------------------ fit + proposal + MH ratio
+template <typename R>
+struct StepOut {
+    R eta[4];
+    R zp, r;
+    bool accept, converged;
+    int evals;
+};
+
+// z_init, init2/init3 (sinh start for log d, e), z_prop, u are the step's variates
+// (reference draw order: klhr.py:129,180,188 ; klhr_sinh.py:184,191,246,255).
+template <typename R, typename Model, int n>
+__device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams& fp, int lane, unsigned m,
+                                R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o) {
+    R xi, tau0;
+    int nev1, nev2;
+    stage1_mode<R, Model>(cf, z_init, fp, lane, m, xi, tau0, nev1);
+    R eta[n];
+    eta[0] = xi;
+    eta[1] = tau0;
+    if constexpr (n == 4) {
+        eta[2] = init2 * (R)fp.initscale;          // klhr_sinh.py:191-193
+        eta[3] = init3 * (R)fp.initscale;
+    }
+    bool conv;
+    stage2_newton<R, Model, n>(cf, eta, fp, lane, m, nev2, conv);
+    R zp, lq0, lq1;
+    if constexpr (n == 2) {
+        const R c = (R)fp.scale_clip;
+        const R s = r_exp(r_clamp(eta[1], -c, c));
+        zp = eta[0] + s * z_prop;                   // klhr.py:180
+        lq0 = logq_gauss<R>(R(0), eta, fp);
+        lq1 = logq_gauss<R>(zp, eta, fp);
+    } else {
+        zp = transport_sinh<R>(z_prop, eta, fp);    // klhr_sinh.py:246
+        lq0 = logq_sinh<R>(R(0), eta, fp);
+        lq1 = logq_sinh<R>(zp, eta, fp);
+    }
+    const Jet<R> Jz = Model::eval(cf, zp);
+    const R r = Jz.l + lq0 - lq1;                   // klhr.py:183-186 with lp(theta) = l(0)
+    const R rm = r < R(0) ? r : R(0);               // np.minimum(0, r); NaN falls through to reject
+    o.accept = (r == r) && (r_log(u) < rm);
+#pragma unroll
+    for (int i = 0; i < n; ++i) o.eta[i] = eta[i];
+    o.zp = zp;
+    o.r = r;
+    o.converged = conv;
+    o.evals = nev1 + nev2 * fp.N + 2;
+}
+
+}  // namespace klhr

@@ -1,0 +1,328 @@
+// klhr_b200 -- target densities as hand-written device functions (replaces BridgeStan).
+//
+// Each model provides
+//   setup(th, rh, lane, mask, mp) -> Coef   octet-cooperative reductions over the D-vector
+//                                           (th = theta row, rh = rho row, both in shared
+//                                           memory), result uniform across the 8 lanes;
+//   eval(coef, y) -> Jet                    O(1): l(y) - l(0), l'(y), l''(y) of the line
+//                                           restriction l(y) = lp(theta + y rho);
+//   lp_grad(th, g, lane, mask, mp) -> lp    full-D log density and gradient (the
+//                                           log_density[_gradient] API, bsmodel.py:15-30).
+// The reference evaluates lp at every quadrature node through the full D-vector
+// (klhr.py:110-113); every named Stan program has a closed-form restriction to a line, so
+// the kernels pay O(D) once per draw and O(1) per evaluation.
+// Conventions: BridgeStan propto=True, jacobian=True (bsmodel.py:18,27 forward no kwargs).
+#pragma once
+#include "klhr_common.cuh"
+#include "../../include/klhr_sm100.h"
+
+namespace klhr {
+
+struct ModelParams {
+    int id;            // KLHR_MODEL_*
+    int D;             // model.dim()
+    int i0, i1;        // funnel: Da ; arK: K, n = T-K ; rosenbrock: Dh
+    double s0, s1;     // ar1: alpha, 1/beta^2
+    const void* p0;    // ill-normal: inv_s2[D] ; corr-normal: P[D*D] ; arK: pack[G|c|yy]
+    const void* p1;
+};
+
+// ------------------------------------------------------------------ quadratic line
+template <typename R>
+struct QuadCoef { R A, Bq; };          // l(y) - l(0) = Bq y - A y^2 / 2
+
+template <typename R>
+__device__ __forceinline__ Jet<R> quad_eval(const QuadCoef<R>& c, R y) {
+    return jet_guard<R>(y * (c.Bq - R(0.5) * c.A * y), c.Bq - c.A * y, -c.A);
+}
+
+// ---- stan/normal.stan:1-9 and stan/ill-normal.stan:1-12  (diagonal Gaussian)
+template <typename R, bool kScaled>
+struct DiagNormal {
+    using Coef = QuadCoef<R>;
+    __device__ static __forceinline__ R wgt(int i, const ModelParams& mp) {
+        return kScaled ? __ldg(reinterpret_cast<const R*>(mp.p0) + i) : R(1);
+    }
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        R a = 0, b = 0;
+        for (int i = lane; i < mp.D; i += kOct) {
+            const R r = rh[i], t = th[i], w = wgt(i, mp);
+            a += r * r * w;
+            b -= r * t * w;
+        }
+        Coef c;
+        c.A = oct_sum(a, m);
+        c.Bq = oct_sum(b, m);
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        R acc = 0;
+        for (int i = lane; i < mp.D; i += kOct) {
+            const R gi = -th[i] * wgt(i, mp);
+            if (g) g[i] = gi;
+            acc += th[i] * gi;
+        }
+        return R(0.5) * oct_sum(acc, m);
+    }
+};
+
+// ---- stan/corr-normal.stan:1-20  (dense precision P = Sigma^-1, symmetric)
+template <typename R>
+struct CorrNormal {
+    using Coef = QuadCoef<R>;
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        const R* P = reinterpret_cast<const R*>(mp.p0);
+        const int D = mp.D;
+        R a = 0, b = 0;
+        for (int i = lane; i < D; i += kOct) {
+            R v = 0;                                      // v_i = (P rho)_i ; P symmetric -> column walk is coalesced
+            for (int k = 0; k < D; ++k) v += __ldg(P + (size_t)k * D + i) * rh[k];
+            a += rh[i] * v;
+            b -= th[i] * v;
+        }
+        Coef c;
+        c.A = oct_sum(a, m);
+        c.Bq = oct_sum(b, m);
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        const R* P = reinterpret_cast<const R*>(mp.p0);
+        const int D = mp.D;
+        R acc = 0;
+        for (int i = lane; i < D; i += kOct) {
+            R v = 0;
+            for (int k = 0; k < D; ++k) v += __ldg(P + (size_t)k * D + i) * th[k];
+            if (g) g[i] = -v;
+            acc -= th[i] * v;
+        }
+        return R(0.5) * oct_sum(acc, m);
+    }
+};
+
+// ---- stan/ar1.stan:1-14   e_t(v) = v_t - alpha v_{t-1}
+template <typename R>
+struct AR1 {
+    using Coef = QuadCoef<R>;
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        const R al = (R)mp.s0, ib2 = (R)mp.s1;
+        R a = 0, b = 0;
+        for (int i = lane; i < mp.D; i += kOct) {
+            if (i == 0) {
+                a += rh[0] * rh[0];
+                b -= rh[0] * th[0];
+            } else {
+                const R er = rh[i] - al * rh[i - 1];
+                const R et = th[i] - al * th[i - 1];
+                a += ib2 * er * er;
+                b -= ib2 * er * et;
+            }
+        }
+        Coef c;
+        c.A = oct_sum(a, m);
+        c.Bq = oct_sum(b, m);
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        const R al = (R)mp.s0, ib2 = (R)mp.s1;
+        const int D = mp.D;
+        R acc = 0;
+        for (int i = lane; i < D; i += kOct) {
+            R gi;
+            if (i == 0) {
+                acc -= R(0.5) * th[0] * th[0];
+                gi = -th[0];
+            } else {
+                const R e = th[i] - al * th[i - 1];
+                acc -= R(0.5) * ib2 * e * e;
+                gi = -ib2 * e;
+            }
+            if (i + 1 < D) gi += ib2 * al * (th[i + 1] - al * th[i]);
+            if (g) g[i] = gi;
+        }
+        return oct_sum(acc, m);
+    }
+};
+
+// ---- stan/funnel.stan:1-11   params [x, alpha_1..alpha_Da]
+template <typename R>
+struct Funnel {
+    struct Coef { R x0, r0, a0, a1, a2, hd, l0; };
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        R a0 = 0, a1 = 0, a2 = 0;
+        for (int i = 1 + lane; i < mp.D; i += kOct) {
+            const R t = th[i], r = rh[i];
+            a0 += t * t;
+            a1 += t * r;
+            a2 += r * r;
+        }
+        Coef c;
+        c.a0 = oct_sum(a0, m);
+        c.a1 = oct_sum(a1, m);
+        c.a2 = oct_sum(a2, m);
+        c.x0 = th[0];
+        c.r0 = rh[0];
+        c.hd = R(0.5) * (R)mp.i0;
+        c.l0 = -c.x0 * c.x0 / R(18) - c.hd * c.x0 - R(0.5) * r_exp(-c.x0) * c.a0;
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) {
+        const R x = c.x0 + y * c.r0;
+        const R ex = r_exp(-x);
+        const R S = c.a0 + y * (R(2) * c.a1 + y * c.a2);
+        const R S1 = R(2) * (c.a1 + y * c.a2);
+        const R S2 = R(2) * c.a2;
+        const R l = -x * x / R(18) - c.hd * x - R(0.5) * ex * S - c.l0;
+        const R l1 = -c.r0 * x / R(9) - c.hd * c.r0 - R(0.5) * ex * (S1 - c.r0 * S);
+        const R l2 = -c.r0 * c.r0 / R(9) - R(0.5) * ex * (c.r0 * c.r0 * S - R(2) * c.r0 * S1 + S2);
+        return jet_guard<R>(l, l1, l2);
+    }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        const R x = th[0];
+        const R ex = r_exp(-x);
+        R ss = 0;
+        for (int i = 1 + lane; i < mp.D; i += kOct) {
+            ss += th[i] * th[i];
+            if (g) g[i] = -th[i] * ex;
+        }
+        ss = oct_sum(ss, m);
+        const R hd = R(0.5) * (R)mp.i0;
+        if (g && lane == 0) g[0] = -x / R(9) - hd + R(0.5) * ex * ss;
+        return -x * x / R(18) - hd * x - R(0.5) * ex * ss;
+    }
+};
+
+// ---- stan/rosenbrock.stan:1-12   params [v_1..v_Dh, t_1..t_Dh]
+template <typename R>
+struct Rosenbrock {
+    struct Coef { R b1, b2, b3, b4; };      // l(y) - l(0) = b1 y + b2 y^2 + b3 y^3 + b4 y^4
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        const int Dh = mp.i0;
+        R p1 = 0, p2 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+        for (int i = lane; i < Dh; i += kOct) {
+            const R v = th[i], t = th[Dh + i], rv = rh[i], rt = rh[Dh + i];
+            const R c0 = t - v * v, c1 = rt - R(2) * v * rv, c2 = -rv * rv;
+            p1 += (v - R(1)) * rv;
+            p2 += rv * rv;
+            q1 += c0 * c1;
+            q2 += c1 * c1 + R(2) * c0 * c2;
+            q3 += c1 * c2;
+            q4 += c2 * c2;
+        }
+        p1 = oct_sum(p1, m); p2 = oct_sum(p2, m);
+        q1 = oct_sum(q1, m); q2 = oct_sum(q2, m); q3 = oct_sum(q3, m); q4 = oct_sum(q4, m);
+        Coef c;
+        c.b1 = -p1 - R(100) * q1;
+        c.b2 = -R(0.5) * p2 - R(50) * q2;
+        c.b3 = -R(100) * q3;
+        c.b4 = -R(50) * q4;
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) {
+        const R l = y * (c.b1 + y * (c.b2 + y * (c.b3 + y * c.b4)));
+        const R l1 = c.b1 + y * (R(2) * c.b2 + y * (R(3) * c.b3 + y * R(4) * c.b4));
+        const R l2 = R(2) * c.b2 + y * (R(6) * c.b3 + y * R(12) * c.b4);
+        return jet_guard<R>(l, l1, l2);
+    }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        const int Dh = mp.i0;
+        R acc = 0;
+        for (int i = lane; i < Dh; i += kOct) {
+            const R v = th[i], t = th[Dh + i];
+            const R c = t - v * v;
+            acc -= R(0.5) * (v - R(1)) * (v - R(1)) + R(50) * c * c;
+            if (g) {
+                g[i] = -(v - R(1)) + R(200) * v * c;
+                g[Dh + i] = -R(100) * c;
+            }
+        }
+        return oct_sum(acc, m);
+    }
+};
+
+// ---- stan/arK.stan:1-20   unconstrained [alpha, beta_1..beta_K, u = log sigma]
+// Sufficient statistics (host, fp64): X_t = (1, y_{t-K..t-1}), G = X^T X, c = X^T y, yy = y^T y
+// over t = K+1..T, packed [G (K+1)^2 | c (K+1) | yy].  sum r^2 = yy - 2 phi.c + phi^T G phi.
+template <typename R>
+struct ARK {
+    struct Coef { R p0, p1, p2, q0, q1, q2, u0, ru, nm1, l0; };
+    __device__ static __forceinline__ void gram_forms(const R* th, const R* rh, int lane, unsigned m,
+                                                      const ModelParams& mp, R& q0, R& q1, R& q2,
+                                                      R& p0, R& p1, R& p2, R* gphi /*(G phi - c)_lane or null*/) {
+        const int K1 = mp.i0 + 1;
+        const R* G = reinterpret_cast<const R*>(mp.p0);
+        const R* cv = G + K1 * K1;
+        const R yy = __ldg(cv + K1);
+        R s_pc = 0, s_pGp = 0, s_rGp = 0, s_rGr = 0, s_rc = 0, pp = 0, pr = 0, rr = 0;
+        for (int i = lane; i < K1; i += kOct) {
+            R Gp = 0, Gr = 0;
+            for (int k = 0; k < K1; ++k) {
+                const R gik = __ldg(G + i * K1 + k);
+                Gp += gik * th[k];
+                Gr += gik * rh[k];
+            }
+            const R ci = __ldg(cv + i);
+            s_pc += th[i] * ci;
+            s_pGp += th[i] * Gp;
+            s_rGp += rh[i] * Gp;
+            s_rGr += rh[i] * Gr;
+            s_rc += rh[i] * ci;
+            pp += th[i] * th[i];
+            pr += th[i] * rh[i];
+            rr += rh[i] * rh[i];
+            if (gphi) gphi[i] = Gp - ci;
+        }
+        s_pc = oct_sum(s_pc, m); s_pGp = oct_sum(s_pGp, m); s_rGp = oct_sum(s_rGp, m);
+        s_rGr = oct_sum(s_rGr, m); s_rc = oct_sum(s_rc, m);
+        p0 = oct_sum(pp, m); p1 = oct_sum(pr, m); p2 = oct_sum(rr, m);
+        q0 = yy - R(2) * s_pc + s_pGp;          // sum r^2 at phi
+        q1 = s_rGp - s_rc;                      // 1/2 d/dy sum r^2
+        q2 = s_rGr;
+    }
+    __device__ static __forceinline__ R value(const Coef& c, R y) {
+        const R u = c.u0 + y * c.ru;
+        return -R(0.5) * (c.p0 + y * (R(2) * c.p1 + y * c.p2)) - R(0.5) * r_exp(R(2) * u) - c.nm1 * u
+               - R(0.5) * r_exp(-R(2) * u) * (c.q0 + y * (R(2) * c.q1 + y * c.q2));
+    }
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        Coef c;
+        gram_forms(th, rh, lane, m, mp, c.q0, c.q1, c.q2, c.p0, c.p1, c.p2, nullptr);
+        c.u0 = th[mp.D - 1];
+        c.ru = rh[mp.D - 1];
+        c.nm1 = (R)(mp.i1 - 1);                 // (T-K) u - u  (likelihood minus Jacobian)
+        c.l0 = 0;
+        c.l0 = value(c, R(0));
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) {
+        const R u = c.u0 + y * c.ru;
+        const R e2 = r_exp(R(2) * u), em2 = r_exp(-R(2) * u);
+        const R S = c.q0 + y * (R(2) * c.q1 + y * c.q2);
+        const R S1 = R(2) * (c.q1 + y * c.q2);
+        const R S2 = R(2) * c.q2;
+        const R l = -R(0.5) * (c.p0 + y * (R(2) * c.p1 + y * c.p2)) - R(0.5) * e2 - c.nm1 * u
+                    - R(0.5) * em2 * S - c.l0;
+        const R l1 = -(c.p1 + y * c.p2) - c.ru * e2 - c.nm1 * c.ru - R(0.5) * em2 * (S1 - R(2) * c.ru * S);
+        const R l2 = -c.p2 - R(2) * c.ru * c.ru * e2
+                     - R(0.5) * em2 * (R(4) * c.ru * c.ru * S - R(4) * c.ru * S1 + S2);
+        return jet_guard<R>(l, l1, l2);
+    }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        // rho := theta is a harmless stand-in for the unused direction sums
+        R q0, q1, q2, p0, p1, p2;
+        const int K1 = mp.i0 + 1;
+        const R u = th[mp.D - 1];
+        const R e2 = r_exp(R(2) * u), em2 = r_exp(-R(2) * u);
+        gram_forms(th, th, lane, m, mp, q0, q1, q2, p0, p1, p2, g);
+        // p0 counted the first K+1 entries only (phi); gphi holds (G phi - c)_i = -(X^T r)_i
+        if (g) {
+            for (int i = lane; i < K1; i += kOct) g[i] = -th[i] - em2 * g[i];
+            if (lane == 0) g[mp.D - 1] = -e2 + R(1) - (R)mp.i1 + em2 * q0;
+        }
+        return -R(0.5) * p0 - R(0.5) * e2 + u - (R)mp.i1 * u - R(0.5) * em2 * q0;
+    }
+};
+
+}  // namespace klhr

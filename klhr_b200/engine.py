@@ -1,0 +1,204 @@
+"""Thin host layer over the C ABI: descriptors, launches, trace buffers.
+
+Nothing here computes on the CPU: tensors are allocated by PyTorch on the CUDA device and
+handed to ``libklhr_sm100.so`` by pointer.  The samplers (``klhr.py``, ``klhr_sinh.py``)
+are built on these three calls:
+
+    step_replay(...)   one draw for every chain with injected rho / variates
+    run(...)           n draws for every chain with in-kernel Philox streams
+    outer_accumulate() pooled second moments for the adaptation PCA
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+from numpy.polynomial.hermite import hermgauss
+
+from . import _lib
+from .bsmodel import BSModel, _dtype_code
+
+
+def gauss_hermite(N: int):
+    """Probabilists' Gauss-Hermite table with sum(w) = 1 (reference ``klhr.py:46-49``)."""
+    x, w = hermgauss(N)
+    return x * np.sqrt(2), w / np.sqrt(np.pi)
+
+
+@dataclass
+class FitConfig:
+    """Reference constructor arguments that reach the fit plus the fixed iteration budget
+    replacing ``scipy.optimize.minimize`` (DESIGN.md "Optimiser")."""
+    family: str = "gauss"
+    N: int = 8
+    initscale: float = 0.1
+    tol: float = 1e-12
+    scale_clip: float = 600.0
+    n1: int = 12
+    n2: int = 24
+    nb: int = 8
+    gtol1: float = 1e-8
+    gtol2: float = 1e-10
+    step_cap: float = 2.0
+    c1: float = 1e-4
+    basin: float = 1e-3
+    x: np.ndarray = field(default=None, repr=False)
+    w: np.ndarray = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.family not in ("gauss", "sinh"):
+            raise ValueError("family must be 'gauss' or 'sinh'")
+        if not 1 <= self.N <= _lib.MAX_NODES:
+            raise ValueError(f"N must be in 1..{_lib.MAX_NODES}")
+        if self.x is None or self.w is None:
+            self.x, self.w = gauss_hermite(self.N)
+
+    def for_dtype(self, dtype):
+        """Convergence thresholds scaled to the arithmetic type."""
+        if dtype == torch.float32:
+            return FitConfig(**{**self.__dict__, "gtol1": max(self.gtol1, 1e-4),
+                                "gtol2": max(self.gtol2, 2e-5)})
+        return self
+
+    def descriptor(self):
+        d = _lib.FitDesc(family=_lib.FAMILY_GAUSS if self.family == "gauss" else _lib.FAMILY_SINH,
+                         n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
+                         initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
+                         gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
+                         basin=self.basin)
+        for i in range(self.N):
+            d.x[i] = float(self.x[i])
+            d.w[i] = float(self.w[i])
+        return d
+
+    @property
+    def n_eta(self):
+        return 2 if self.family == "gauss" else 4
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _require_cuda(t, name):
+    if not (torch.is_tensor(t) and t.is_cuda and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous CUDA tensor")
+
+
+class Trace:
+    """Per-draw trace buffers [S, B, ...] allocated on the device."""
+
+    def __init__(self, S, B, D, n_eta, dtype, device, variates=False, rho=True):
+        z = lambda *shape, dt=dtype: torch.zeros(*shape, dtype=dt, device=device)
+        self.eta = z(S, B, n_eta)
+        self.zp = z(S, B)
+        self.r = z(S, B)
+        self.accept = z(S, B, dt=torch.int32)
+        self.evals = z(S, B, dt=torch.int32)
+        self.rho = z(S, B, D) if rho else None
+        self.z_init = z(S, B) if variates else None
+        self.z_prop = z(S, B) if variates else None
+        self.u = z(S, B) if variates else None
+        self.init4 = z(S, B, 4) if variates and n_eta == 4 else None
+
+    def descriptor(self):
+        return _lib.TraceDesc(eta=_ptr(self.eta), zp=_ptr(self.zp), r=_ptr(self.r), accept=_ptr(self.accept),
+                              evals=_ptr(self.evals), rho=_ptr(self.rho), z_init=_ptr(self.z_init),
+                              z_prop=_ptr(self.z_prop), u=_ptr(self.u), init4=_ptr(self.init4))
+
+
+def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, init4=None, trace=True):
+    """One draw for every chain with host-injected direction and variates; ``theta`` (B, D)
+    is advanced IN PLACE.  Returns a ``Trace`` (S = 1) or None."""
+    lib = _lib.load()
+    for t, n in ((theta, "theta"), (rho, "rho"), (z_init, "z_init"), (z_prop, "z_prop"), (u, "u")):
+        _require_cuda(t, n)
+    B, D = theta.shape
+    if D != model.dim():
+        raise ValueError("theta does not match model.dim()")
+    dtype, dev = theta.dtype, theta.device
+    if fit.family == "sinh":
+        if init4 is None:
+            raise ValueError("sinh family needs init4")
+        _require_cuda(init4, "init4")
+    tr = Trace(1, B, D, fit.n_eta, dtype, dev, rho=False) if trace else None
+    trd = tr.descriptor() if tr else None
+    md, fd = model.descriptor(dtype, dev), fit.descriptor()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.klhr_step_replay(C.byref(md), C.byref(fd), _dtype_code(dtype), theta.data_ptr(),
+                                        rho.data_ptr(), z_init.data_ptr(), _ptr(init4), z_prop.data_ptr(),
+                                        u.data_ptr(), C.byref(trd) if trd else None, B, st),
+                   "klhr_step_replay")
+    return tr
+
+
+@dataclass
+class Direction:
+    """Device-resident direction law (reference ``_random_direction``, klhr.py:143-153)."""
+    mean_cols: torch.Tensor = None     # (n_cols, D) or None (zero mean)
+    sd: torch.Tensor = None            # (D,) sqrt(_cov) or None (ones)
+    cdf: torch.Tensor = None           # (n_cols,) cumulative column probabilities
+
+    def descriptor(self):
+        n = 0 if self.mean_cols is None else int(self.mean_cols.shape[0])
+        return _lib.DirectionDesc(mean_cols=_ptr(self.mean_cols), sd=_ptr(self.sd), cdf=_ptr(self.cdf),
+                                  n_cols=n)
+
+
+def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Direction = None,
+        chain_offset=0, draw_offset=0, *, shift=None, pooled_s1=None, pooled_s2=None, chain_s1=None,
+        chain_s2=None, accept_count=None, evals_total=None, draws=None, thin=1, skip_accum_last=False,
+        trace: Trace = None):
+    """``n_steps`` draws for every chain, in place on ``theta`` (B, D), asynchronous on the
+    current stream.  All keyword tensors are optional device accumulators (see
+    ``klhr_accum_t`` in include/klhr_sm100.h)."""
+    lib = _lib.load()
+    _require_cuda(theta, "theta")
+    B, D = theta.shape
+    if D != model.dim():
+        raise ValueError("theta does not match model.dim()")
+    dtype, dev = theta.dtype, theta.device
+    md, fd = model.descriptor(dtype, dev), fit.descriptor()
+    dd = (direction or Direction()).descriptor()
+    ad = _lib.AccumDesc(shift=_ptr(shift), pooled_s1=_ptr(pooled_s1), pooled_s2=_ptr(pooled_s2),
+                        chain_s1=_ptr(chain_s1), chain_s2=_ptr(chain_s2), accept_count=_ptr(accept_count),
+                        evals_total=_ptr(evals_total), draws=_ptr(draws), thin=int(thin),
+                        skip_accum_last=1 if skip_accum_last else 0)
+    trd = trace.descriptor() if trace is not None else None
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.klhr_run(C.byref(md), C.byref(fd), C.byref(dd), _dtype_code(dtype), theta.data_ptr(),
+                                B, int(chain_offset), int(draw_offset), int(n_steps),
+                                C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ad),
+                                C.byref(trd) if trd else None, st),
+                   "klhr_run")
+
+
+def outer_accumulate(theta, shift, outer, s1=None):
+    """outer (D, D) += sum_c (theta_c - shift)(theta_c - shift)^T ; s1 (D,) += sum_c (theta_c - shift)."""
+    lib = _lib.load()
+    _require_cuda(theta, "theta")
+    B, D = theta.shape
+    with torch.cuda.device(theta.device):
+        st = torch.cuda.current_stream(theta.device).cuda_stream
+        _lib.check(lib.klhr_outer_accumulate(_dtype_code(theta.dtype), theta.data_ptr(), _ptr(shift),
+                                             outer.data_ptr(), _ptr(s1), B, D, st),
+                   "klhr_outer_accumulate")
+
+
+def launch_info(model: BSModel, fit: FitConfig, dtype=torch.float64, free_running=True, accumulate=False,
+                device=None):
+    """(threads per CTA, dynamic shared bytes, registers per thread, resident CTAs per SM)."""
+    lib = _lib.load()
+    dev = torch.device(device) if device is not None else model.device
+    md, fd = model.descriptor(dtype, dev), fit.descriptor()
+    t, s, r = C.c_int32(), C.c_int32(), C.c_int32()
+    with torch.cuda.device(dev):
+        n = lib.klhr_launch_info(C.byref(md), C.byref(fd), _dtype_code(dtype), int(free_running),
+                                 int(accumulate), C.byref(t), C.byref(s), C.byref(r))
+    if n <= 0:
+        raise _lib.KLHRLibraryError(f"klhr_launch_info failed ({n}): {_lib.last_error()}")
+    return dict(threads=t.value, smem=s.value, regs=r.value, ctas_per_sm=n)
