@@ -110,6 +110,9 @@ typedef struct klhr_accum {
     int32_t thin;                /* write every `thin`-th draw (>= 1)                      */
     int32_t skip_accum_last;     /* 1: the last draw of the launch is a window closure and
                                     is not accumulated (klhr.py:202-221)                   */
+    int64_t thin_offset;         /* draws already taken towards `draws` by earlier launches:
+                                    draw g = thin_offset + step + 1 is stored in row g/thin - 1
+                                    when g % thin == 0, so a sample() may span launches    */
 } klhr_accum_t;
 
 int klhr_abi_version(void);

@@ -50,7 +50,7 @@ class AccumDesc(C.Structure):
     _fields_ = [("shift", C.c_void_p), ("pooled_s1", C.c_void_p), ("pooled_s2", C.c_void_p),
                 ("chain_s1", C.c_void_p), ("chain_s2", C.c_void_p), ("accept_count", C.c_void_p),
                 ("evals_total", C.c_void_p), ("draws", C.c_void_p), ("thin", C.c_int32),
-                ("skip_accum_last", C.c_int32)]
+                ("skip_accum_last", C.c_int32), ("thin_offset", C.c_int64)]
 
 
 EXPORTS = {

@@ -240,9 +240,12 @@ __global__ void __launch_bounds__(kThreadsMax) step_kernel(const __grid_constant
                     }
                 }
             }
-            if (a.acc.draws && ((step + 1) % a.acc.thin == 0)) {
-                R* g = reinterpret_cast<R*>(a.acc.draws) + ((long long)(step / a.acc.thin) * a.B + c) * D;
-                for (int i = lane; i < D; i += kOct) g[i] = th[i];
+            if (a.acc.draws) {
+                const long long gdraw = a.acc.thin_offset + step + 1;
+                if (gdraw % a.acc.thin == 0) {
+                    R* g = reinterpret_cast<R*>(a.acc.draws) + ((gdraw / a.acc.thin - 1) * a.B + c) * D;
+                    for (int i = lane; i < D; i += kOct) g[i] = th[i];
+                }
             }
         }
         // ------------------------------------------------------------------ write back

@@ -150,8 +150,8 @@ class Direction:
 
 def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Direction = None,
         chain_offset=0, draw_offset=0, *, shift=None, pooled_s1=None, pooled_s2=None, chain_s1=None,
-        chain_s2=None, accept_count=None, evals_total=None, draws=None, thin=1, skip_accum_last=False,
-        trace: Trace = None):
+        chain_s2=None, accept_count=None, evals_total=None, draws=None, thin=1, thin_offset=0,
+        skip_accum_last=False, trace: Trace = None):
     """``n_steps`` draws for every chain, in place on ``theta`` (B, D), asynchronous on the
     current stream.  All keyword tensors are optional device accumulators (see
     ``klhr_accum_t`` in include/klhr_sm100.h)."""
@@ -166,7 +166,7 @@ def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Directi
     ad = _lib.AccumDesc(shift=_ptr(shift), pooled_s1=_ptr(pooled_s1), pooled_s2=_ptr(pooled_s2),
                         chain_s1=_ptr(chain_s1), chain_s2=_ptr(chain_s2), accept_count=_ptr(accept_count),
                         evals_total=_ptr(evals_total), draws=_ptr(draws), thin=int(thin),
-                        skip_accum_last=1 if skip_accum_last else 0)
+                        skip_accum_last=1 if skip_accum_last else 0, thin_offset=int(thin_offset))
     trd = trace.descriptor() if trace is not None else None
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream(dev).cuda_stream

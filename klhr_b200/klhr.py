@@ -1,0 +1,241 @@
+"""``KLHR`` -- KL Hit-and-Run with a Gaussian line family, for a batch of chains on B200.
+
+Drop-in for reference ``klhr.py:15-223``: same class name, constructor keywords and
+defaults (klhr.py:16-34), same attributes (``D``, ``theta``, ``acceptance_probability``,
+``grad_evals``, ``_mean``, ``_cov``, ``_eigvecs``, ``_eigvals``) and methods (``draw``,
+``sample``, ``fit``, ``KL``-equivalent fit trace).  Extra keywords: ``chains``, ``dtype``,
+``device``, ``process_group`` and the fixed iteration budget ``fit_budget``.
+
+What runs where
+  * every draw of every chain: ``klhr_run`` (one launch per stretch of draws between
+    adaptation events) -- direction, line fit, proposal, MH, accumulation, all in the kernel;
+  * window closures (klhr.py:202-214, at most ~a dozen per run): pooled raw sums are
+    all-reduced over the process group and turned into ``_mean``, ``_cov``, eigenpairs on the
+    host, identically on every rank.
+
+Documented deviations from the reference (DESIGN.md has the full list)
+  * ``theta=`` is honoured (the reference's ``_initialize`` overwrites it, klhr.py:94);
+  * adaptation pools over chains instead of over one chain's history; the PCA is the
+    eigen-decomposition of the pooled second-moment matrix, sampled every ``pca_stride`` draws;
+  * ``overrelaxed=True`` is not implemented and raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine
+from .adaptation import OnlineMoments, OnlinePCA, WindowedAdaptation, allreduce_adaptation
+from .mcmc import MCMCBase
+
+
+class KLHR(MCMCBase):
+    _family = "gauss"
+    _eigen_weights_normalised = False          # klhr.py:150 sums evals * eigvecs (un-normalised)
+
+    def __init__(self, bsmodel, theta=None, seed=None, N=8, K=10, J=2, l=4, initscale=0.1, warmup=1_000,
+                 windowsize=50, windowscale=2, tol=1e-12, grad_clip=1e15, scale_clip=600,
+                 scale_dir_cov=False, overrelaxed=False, eigen_method_one=True, max_init_tries=100, *,
+                 chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
+                 pca_stride=10, fit_budget=None):
+        super().__init__(bsmodel, -1, theta=theta, seed=seed, chains=chains, dtype=dtype, device=device)
+        if overrelaxed:
+            raise NotImplementedError("over-relaxed proposals are not implemented on the device path "
+                                      "(SURVEY.md section 8f N2); pass overrelaxed=False")
+        self.N, self.K, self.l = N, K, l
+        self.J = self._clip_J(J)
+        self._tol, self._grad_clip, self._scale_clip = tol, grad_clip, scale_clip
+        self._max_init_tries = max_init_tries
+        self._initscale = initscale
+        self.x, self.w = engine.gauss_hermite(N)
+        budget = dict(fit_budget or {})
+        self._fit = engine.FitConfig(family=self._family, N=N, initscale=initscale, tol=tol,
+                                     scale_clip=float(scale_clip), x=self.x, w=self.w,
+                                     **{"n2": 24 if self._family == "gauss" else 48, **budget}).for_dtype(dtype)
+        self._windowedadaptation = WindowedAdaptation(warmup, windowsize=windowsize, windowscale=windowscale)
+        self._scale_dir_cov = scale_dir_cov
+        self._overrelaxed = overrelaxed
+        self._eigen_method_one = eigen_method_one
+        self._pca_stride = max(1, int(pca_stride))
+        self._group = process_group
+        dev = self.device
+        self._onlinemoments = OnlineMoments(self.D, device=dev)
+        self._onlinemoments_density = OnlineMoments(self.D, device=dev)
+        self._onlinepca = OnlinePCA(self.D, K=self.J, l=l, device=dev)
+        self._mean = np.zeros(self.D)
+        self._cov = np.ones(self.D)
+        ncol = self.J + 1 if eigen_method_one else self.J
+        self._eigvecs = np.zeros((self.D, ncol))
+        self._eigvals = np.ones(ncol)
+        self._draw = 0
+        self._accept_count = torch.zeros(self.chains, dtype=torch.int64, device=dev)
+        self._evals_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        if chain_offset is None:
+            chain_offset = 0
+            if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+                chain_offset = torch.distributed.get_rank(process_group) * self.chains
+        self._chain_offset = int(chain_offset)
+        self._shift_dev = torch.zeros(self.D, dtype=dtype, device=dev)
+        self._direction = None
+        self._refresh_direction()
+        if theta is None:
+            self._initialize()
+
+    # ------------------------------------------------------------------ reference quirks kept per class
+    def _clip_J(self, J):
+        return J if J < self.D else self.D - 1                 # klhr.py:39
+
+    # ------------------------------------------------------------------ start points (klhr.py:87-99)
+    def _initialize(self):
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        todo = torch.ones(self.chains, dtype=torch.bool, device=self.device)
+        for _ in range(self._max_init_tries):
+            n = int(todo.sum())
+            if n == 0:
+                return
+            cand = (torch.randn(n, self.D, generator=g, dtype=torch.float64) * self._initscale)
+            cand = cand.to(self.device, self.dtype)
+            lp, grad = self.model.log_density_gradient(cand)
+            ok = torch.isfinite(lp) & torch.isfinite(grad.norm(dim=1))
+            idx = todo.nonzero().squeeze(1)
+            self._theta[idx[ok]] = cand[ok]
+            todo[idx[ok]] = False
+        if bool(todo.any()):
+            raise RuntimeError("failed to initialize")
+
+    # ------------------------------------------------------------------ direction law (klhr.py:143-153)
+    def _refresh_direction(self):
+        dev, dt = self.device, self.dtype
+        lam = np.asarray(self._eigvals, dtype=np.float64)
+        p = lam / np.sum(lam)
+        sd = torch.as_tensor(np.sqrt(np.maximum(self._cov, 0.0)), dtype=dt, device=dev).contiguous()
+        if self._eigen_method_one:
+            cols = torch.as_tensor(np.ascontiguousarray(self._eigvecs.T), dtype=dt, device=dev).contiguous()
+            cdf = np.cumsum(p)
+            cdf /= cdf[-1]
+            cdf_t = torch.as_tensor(cdf, dtype=dt, device=dev).contiguous()
+            self._direction = engine.Direction(mean_cols=cols, sd=sd, cdf=cdf_t)
+        else:
+            wgt = p if self._eigen_weights_normalised else lam
+            m = np.sum(wgt * self._eigvecs, axis=1) if self._eigvecs.shape[1] else np.zeros(self.D)
+            cols = torch.as_tensor(m[None, :], dtype=dt, device=dev).contiguous()
+            self._direction = engine.Direction(mean_cols=cols, sd=sd, cdf=None)
+
+    # ------------------------------------------------------------------ the loop (klhr.py:196-223)
+    def _advance(self, n, draws=None, thin=1, chain_s1=None, chain_s2=None, stat_shift=None):
+        """Advance every chain by ``n`` draws.  ``draws`` (n // thin, B, D) receives thinned
+        states; chain_s1/chain_s2 accumulate per-chain sums (post-warm-up diagnostics)."""
+        wa = self._windowedadaptation
+        done = 0
+        while done < n:
+            nxt = wa.next_closure(self._draw)
+            adapting = nxt is not None
+            steps = n - done
+            closes = False
+            if adapting:
+                steps = min(steps, nxt - self._draw, self._pca_stride)
+                closes = self._draw + steps == nxt
+            kw = {}
+            if adapting:
+                mom = self._onlinemoments
+                kw.update(shift=self._shift_dev, pooled_s1=mom.s1, pooled_s2=mom.s2, skip_accum_last=closes)
+            elif chain_s1 is not None:
+                kw.update(shift=stat_shift, chain_s1=chain_s1, chain_s2=chain_s2)
+            engine.run(self.model, self._fit, self._theta, steps, self.seed, self._direction,
+                       chain_offset=self._chain_offset, draw_offset=self._draw,
+                       accept_count=self._accept_count, evals_total=self._evals_total,
+                       draws=draws, thin=thin, thin_offset=done, **kw)
+            self._draw += steps
+            done += steps
+            if adapting:
+                self._onlinemoments.add_sums(self.chains * (steps - (1 if closes else 0)))
+                if closes:
+                    self._close_window()
+                else:
+                    self._snapshot_update()
+
+    def _snapshot_update(self):
+        """Pooled analogue of klhr.py:216-219 on the current ensemble: PCA second moments of
+        (theta - _mean) and, for ``scale_dir_cov``, gradient moments."""
+        pca = self._onlinepca
+        engine.outer_accumulate(self._theta, self._shift_dev, pca.outer)
+        pca.add_sums(self.chains)
+        if self._scale_dir_cov:
+            _, g = self.model.log_density_gradient(self._theta)
+            self._onlinemoments_density.update(torch.clamp(g, -self._grad_clip, self._grad_clip))
+
+    def _close_window(self):
+        """klhr.py:202-214 with pooled sums; identical result on every rank."""
+        mom, gmom, pca = self._onlinemoments, self._onlinemoments_density, self._onlinepca
+        allreduce_adaptation([mom, gmom], pca, group=self._group)
+        self._mean = mom.mean().cpu().numpy()
+        self._cov = mom.var().cpu().numpy()
+        if self._scale_dir_cov:
+            self._cov = self._cov / (self._tol + gmom.var().cpu().numpy())
+        self._eigvecs[:, :self.J] = pca.vectors()
+        self._eigvals[:self.J] = pca.values()
+        self._shift_dev = torch.as_tensor(self._mean, dtype=self.dtype, device=self.device).contiguous()
+        mean64 = torch.as_tensor(self._mean, dtype=torch.float64, device=self.device)
+        mom.reset(shift=mean64)
+        gmom.reset()
+        pca.reset()
+        self._refresh_direction()
+
+    # ------------------------------------------------------------------ public API
+    def draw(self):
+        self._advance(1)
+        return self.theta
+
+    def sample(self, M, thin=1):
+        """``M`` rows, row 0 the current state (mcmc.py:31-37); ``thin`` keeps every thin-th draw."""
+        out = torch.empty(M, self.chains, self.D, dtype=self.dtype, device=self.device)
+        out[0] = self._theta
+        if M > 1:
+            self._advance((M - 1) * thin, draws=out[1:], thin=thin)
+        if self.chains == 1:
+            return out[:, 0].double().cpu().numpy()
+        return out
+
+    def run(self, n, chain_stats=False):
+        """Advance ``n`` draws without storing them.  With ``chain_stats`` returns per-chain
+        sums ``(s1, s2)`` of shape (B, D) over the draws (for ESS / MCSE, diagnostics.py)."""
+        if not chain_stats:
+            self._advance(n)
+            return None
+        s1 = torch.zeros(self.chains, self.D, dtype=torch.float64, device=self.device)
+        s2 = torch.zeros_like(s1)
+        self._advance(n, chain_s1=s1, chain_s2=s2, stat_shift=None)
+        return s1, s2
+
+    def fit(self, rho, z_init=None):
+        """Line fit through the current state along ``rho`` ((D,) or (B, D)); returns eta
+        ((2,) / (B, 2); (4,) for the sinh family) like reference ``fit`` (klhr.py:126-141).
+        Does not advance the chains."""
+        rho_t = torch.as_tensor(np.asarray(rho.detach().cpu() if torch.is_tensor(rho) else rho,
+                                           dtype=np.float64)).reshape(-1, self.D)
+        rho_t = rho_t.expand(self.chains, self.D).to(self.device, self.dtype).contiguous()
+        B = self.chains
+        z = (torch.as_tensor(self.rng.normal(size=B)) if z_init is None
+             else torch.as_tensor(np.broadcast_to(np.asarray(z_init, dtype=np.float64), (B,)).copy()))
+        z = z.to(self.device, self.dtype).contiguous()
+        zeros = torch.zeros(B, dtype=self.dtype, device=self.device)
+        half = torch.full((B,), 0.5, dtype=self.dtype, device=self.device)
+        init4 = None
+        if self._family == "sinh":
+            init4 = torch.as_tensor(self.rng.normal(size=(B, 4))).to(self.device, self.dtype).contiguous()
+        scratch = self._theta.clone()
+        tr = engine.step_replay(self.model, self._fit, scratch, rho_t, z, zeros, half, init4=init4)
+        eta = tr.eta[0]
+        return eta[0].double().cpu().numpy() if self.chains == 1 else eta
+
+    @property
+    def acceptance_probability(self):
+        """Mean accept rate over all chains and draws (running mean of klhr.py:192-193)."""
+        if self._draw == 0:
+            return 0.0
+        return float(self._accept_count.double().mean()) / self._draw
+
+    @property
+    def grad_evals(self):
+        """Line evaluations executed, summed over chains (klhr.py:132,140 counts model calls)."""
+        return int(self._evals_total.item())

@@ -1,0 +1,38 @@
+"""``KLHRSINH`` -- KL Hit-and-Run with the 4-parameter sinh-arcsinh line family.
+
+Drop-in for reference ``klhr_sinh.py:14-289``: constructor keywords and defaults of
+klhr_sinh.py:15-32 (``tol=1e-10``, ``scale_clip=300``, ``eigen_method_one=False``), no
+clipping of ``J`` (:37) and normalised eigenvalue weights in the method-two direction mean
+(:210).  ``overrelaxed`` defaults to True in the reference (:30); the over-relaxed proposal
+draws from SciPy's global RNG and is not on the device path, so
+the default here is False and True raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from .klhr import KLHR
+
+
+class KLHRSINH(KLHR):
+    _family = "sinh"
+    _eigen_weights_normalised = True           # klhr_sinh.py:210 uses p = evals / sum(evals)
+
+    def __init__(self, bsmodel, theta=None, seed=None, N=8, K=10, J=2, l=4, initscale=0.1, warmup=1_000,
+                 windowsize=50, windowscale=2, tol=1e-10, grad_clip=1e15, scale_clip=300,
+                 scale_dir_cov=False, overrelaxed=False, eigen_method_one=False, max_init_tries=100, *,
+                 chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
+                 pca_stride=10, fit_budget=None):
+        if dtype != torch.float64:
+            raise TypeError("the sinh-arcsinh family needs float64 (sinh/cosh of up to +-300, "
+                            "klhr_sinh.py:100-110)")
+        super().__init__(bsmodel, theta=theta, seed=seed, N=N, K=K, J=J, l=l, initscale=initscale,
+                         warmup=warmup, windowsize=windowsize, windowscale=windowscale, tol=tol,
+                         grad_clip=grad_clip, scale_clip=scale_clip, scale_dir_cov=scale_dir_cov,
+                         overrelaxed=overrelaxed, eigen_method_one=eigen_method_one,
+                         max_init_tries=max_init_tries, chains=chains, dtype=dtype, device=device,
+                         process_group=process_group, chain_offset=chain_offset, pca_stride=pca_stride,
+                         fit_budget=fit_budget)
+
+    def _clip_J(self, J):
+        return J                                # klhr_sinh.py:37 does not clip

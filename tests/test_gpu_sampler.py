@@ -1,0 +1,212 @@
+"""Free-running sampler on the GPU: in-kernel Philox streams, posterior and acceptance parity
+(north star tests 2 and 3), adaptation, API shapes."""
+import numpy as np
+import pytest
+import torch
+
+import klhr_b200 as kb
+from conftest import load_tape
+from gpu_util import device, fit_pair, up
+from klhr_b200.diagnostics import chain_summary
+from oracle import batched, stan_models
+
+pytestmark = pytest.mark.gpu
+
+
+def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, direction=None):
+    model = kb.BSModel(stan_file=f"stan/{model_name}.stan", data=data, device=device())
+    kfit, ofit = fit_pair(family, dtype)
+    D = model.dim()
+    rng = np.random.default_rng(seed)
+    theta0 = rng.normal(size=(B, D)) * 0.3
+    th = up(theta0, dtype)
+    tr = kb.Trace(S, B, D, kfit.n_eta, dtype, device(), variates=True, rho=True)
+    kb.run(model, kfit, th, S, seed, direction, trace=tr)
+    torch.cuda.synchronize()
+    return model, ofit, theta0, th, tr
+
+
+@pytest.mark.parametrize("model_name,data,family", [
+    ("ill-normal", {"D": 100}, "gauss"), ("funnel", {"D": 4}, "gauss"), ("funnel", {"D": 1}, "sinh"),
+    ("rosenbrock", {"D": 2}, "gauss"), ("ar1", {"N": 20}, "gauss")])
+def test_free_running_step_equals_oracle_on_emitted_variates(model_name, data, family):
+    """The free-running kernel emits the direction and variates it drew; replaying them through
+    the oracle must give the same fit, proposal, ratio, flag and state (fp64, 1e-10)."""
+    B, S = 512, 3
+    model, ofit, theta0, th, tr = _trace_run(model_name, data, family, B, S)
+    om = stan_models.make_model(model_name, data)
+    theta = theta0.copy()
+    for s in range(S):
+        g = lambda t: t[s].double().cpu().numpy()
+        ref = batched.step(om, theta, g(tr.rho), g(tr.z_init), g(tr.z_prop), g(tr.u), ofit,
+                           init4=g(tr.init4) if tr.init4 is not None else None)
+        sc = np.exp(np.clip(ref["eta"][:, 1], -300, 300))
+        conv = ref["converged"]
+        em = np.abs(g(tr.eta)[:, 0] - ref["eta"][:, 0]) / np.maximum(sc, np.abs(ref["eta"][:, 0]))
+        es = np.abs(g(tr.eta)[:, 1:] - ref["eta"][:, 1:]).max(1)
+        if family == "gauss":
+            assert em.max() <= 1e-10 and es.max() <= 1e-10
+            assert np.array_equal(tr.accept[s].cpu().numpy().astype(bool), ref["accept"])
+            theta = ref["theta"]
+        else:
+            assert (np.maximum(em, es)[conv] <= 1e-10).mean() >= 0.98
+            # continue from the device state so rare path differences do not compound
+            acc = tr.accept[s].cpu().numpy().astype(bool)
+            theta = np.where(acc[:, None], theta + g(tr.zp)[:, None] * g(tr.rho), theta)
+    if family == "gauss":
+        assert np.allclose(th.cpu().numpy(), theta, rtol=1e-10, atol=1e-10)
+
+
+def test_philox_streams_are_standard_and_reproducible():
+    """Variates: N(0,1) normals, U(0,1) uniforms, unit directions; independent of sharding."""
+    B, S = 4096, 4
+    _, _, _, th_a, tr = _trace_run("normal", {"D": 64}, "gauss", B, S, seed=11)
+    z = torch.cat([tr.z_init.flatten(), tr.z_prop.flatten()]).cpu().numpy()
+    u = tr.u.flatten().cpu().numpy()
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs(np.mean(z ** 4) - 3) < 0.2
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 4 / np.sqrt(12 * u.size)
+    rho = tr.rho.reshape(-1, 64).cpu().numpy()
+    assert np.allclose(np.linalg.norm(rho + 1e-12, axis=1), 1, atol=1e-12)
+    comp = rho.flatten() * 8.0                      # sqrt(D) * component ~ N(0,1) approximately
+    assert abs(comp.mean()) < 5 / np.sqrt(comp.size) and abs(comp.var() - 1) < 0.01
+    # isotropy: every coordinate carries 1/D of the squared norm
+    assert np.allclose((rho ** 2).mean(0), 1 / 64, rtol=0.08)
+    # the stream of chain c at draw t depends only on (seed, chain id, draw index):
+    model = kb.BSModel(stan_file="stan/normal.stan", data={"D": 64}, device=device())
+    kfit, _ = fit_pair("gauss")
+    rng = np.random.default_rng(11)
+    theta0 = rng.normal(size=(B, 64)) * 0.3
+    lo, hi = up(theta0[:1000]), up(theta0[1000:])
+    for t in range(S):                               # split over chains AND over launches
+        kb.run(model, kfit, lo, 1, 11, chain_offset=0, draw_offset=t)
+        kb.run(model, kfit, hi, 1, 11, chain_offset=1000, draw_offset=t)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([lo, hi]), th_a)
+
+
+def test_posterior_ill_normal_within_4_mcse():
+    """North-star posterior test: means and variances within 4 MCSE of the truth
+    (stan/ill-normal.stan:5: var_i = i^2 / D)."""
+    D, B = 100, 4096
+    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": D}, device=device())
+    s = kb.KLHR(model, seed=3, chains=B, warmup=1000)
+    s.run(1000)
+    assert s._windowedadaptation.closures == [50, 150, 350, 1000]
+    s.run(3000)                                          # let the slow coordinates mix
+    S = 4000
+    s1, s2 = s.run(S, chain_stats=True)
+    summ = chain_summary(s1, s2, S)
+    truth = torch.arange(1, D + 1, dtype=torch.float64, device=device()) ** 2 / D
+    zm = summ["mean"].abs() / summ["mcse_mean"]
+    zv = (summ["var"] - truth).abs() / summ["mcse_var"]
+    assert float(zm.max()) < 4.5 and float((zm > 4).float().mean()) <= 0.02
+    assert float(zv.max()) < 4.5 and float((zv > 4).float().mean()) <= 0.02
+    assert s.acceptance_probability > 0.9999            # Gaussian target: acceptance == 1
+    assert float(summ["rhat"].max()) < 1.05
+
+
+def test_acceptance_rate_matches_reference_tape():
+    """North-star acceptance test: funnel (dims 2), Gaussian family; the reference tape's rate
+    and the device rate agree within 4 binomial standard errors of the tape."""
+    t, meta, data = load_tape("funnel_d2_klhr")
+    n_ref = len(t["accept"]) - 1000
+    p_ref = t["accept"][1000:].mean()                    # post-warm-up draws of the reference chain
+    model = kb.BSModel(stan_file="stan/funnel.stan", data=data, device=device())
+    s = kb.KLHR(model, seed=5, chains=8192, warmup=1000)
+    s.run(1000)
+    a0 = s._accept_count.clone()
+    s.run(500)
+    p_dev = float((s._accept_count - a0).double().mean()) / 500
+    se = np.sqrt(p_ref * (1 - p_ref) / n_ref)
+    assert abs(p_dev - p_ref) <= 4 * se, (p_dev, p_ref, se)
+
+
+def test_funnel_sinh_posterior_marginal():
+    """reference experiment_funnel.py:66-70: the first funnel coordinate is N(0, 3^2)."""
+    model = kb.BSModel(stan_file="stan/funnel.stan", data={"D": 1}, device=device())
+    s = kb.KLHRSINH(model, seed=9, chains=8192, warmup=400, overrelaxed=False)
+    s.run(400)
+    s.run(600)
+    S = 1500
+    s1, s2 = s.run(S, chain_stats=True)
+    summ = chain_summary(s1, s2, S)
+    assert abs(float(summ["mean"][0])) < 5 * float(summ["mcse_mean"][0]) + 0.02
+    assert abs(float(summ["var"][0]) - 9.0) < 5 * float(summ["mcse_var"][0]) + 0.25
+    assert 0.85 < s.acceptance_probability < 1.0
+
+
+def test_sampler_api_matches_reference_surface():
+    model = kb.BSModel(stan_file="stan/normal.stan", data={"D": 2}, device=device())
+    s = kb.KLHR(model, seed=1)                           # one chain: NumPy in / out like the reference
+    assert s.D == 2 and s.theta.shape == (2,) and isinstance(s.theta, np.ndarray)
+    th = s.draw()
+    assert th.shape == (2,) and s._draw == 1
+    out = s.sample(50)
+    assert out.shape == (50, 2) and out.dtype == np.float64 and np.array_equal(out[-1], s.theta)
+    assert s.acceptance_probability == 1.0 and s.grad_evals > 0
+    eta = s.fit(np.array([1.0, 0.0]))
+    assert eta.shape == (2,) and abs(eta[1]) < 1e-9     # unit normal along any line: s = 1
+    assert next(iter(s)).shape == (2,)
+    b = kb.KLHR(model, seed=1, chains=64)
+    d = b.sample(10, thin=3)
+    assert d.shape == (10, 64, 2) and b._draw == 27 and torch.equal(d[-1], b.theta)
+    with pytest.raises(NotImplementedError):
+        kb.KLHR(model, overrelaxed=True)
+    with pytest.raises(NotImplementedError):
+        kb.BSModel(stan_file="stan/earnings.stan", data={})
+
+
+def test_adaptation_learns_scales_and_leading_direction():
+    """Pooled windowed adaptation: _cov approaches the target variances and the leading
+    eigenvector of corr-normal points along the all-ones-ish dominant mode."""
+    D = 16
+    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": D}, device=device())
+    s = kb.KLHR(model, seed=2, chains=4096, warmup=1000)
+    s.run(1000)
+    truth = np.arange(1, D + 1) ** 2 / D
+    assert np.allclose(s._cov, truth, rtol=0.25)
+    assert np.allclose(s._mean, 0, atol=0.2 * np.sqrt(truth).max())
+    cm = kb.BSModel(stan_file="stan/corr-normal.stan", data={"N": 12, "rho": 0.9}, device=device())
+    c = kb.KLHR(cm, seed=4, chains=4096, warmup=1000)
+    c.run(1000)
+    idx = np.arange(12)
+    w, V = np.linalg.eigh(0.9 ** np.abs(idx[:, None] - idx[None, :]))
+    assert abs(c._eigvecs[:, 0] @ V[:, -1]) > 0.9
+    assert np.isclose(c._eigvals[0], w[-1], rtol=0.3)
+
+
+def test_model_eval_matches_oracle():
+    rng = np.random.default_rng(0)
+    y = stan_models.simulate_ark_series(T=300, seed=5)
+    cases = [("normal", {"D": 5}), ("ill-normal", {"D": 33}), ("funnel", {"D": 6}),
+             ("corr-normal", {"N": 20, "rho": 0.9}), ("ar1", {"N": 17}),
+             ("arK", {"K": 5, "T": 300, "y": y.tolist()}), ("rosenbrock", {"D": 3})]
+    for name, data in cases:
+        m = kb.BSModel(stan_file=f"stan/{name}.stan", data=data, device=device())
+        om = stan_models.make_model(name, data)
+        th = rng.normal(size=(257, m.dim())) * 0.5
+        lp, g = m.log_density_gradient(up(th))
+        rl, rg = om.lp_grad(th)
+        assert np.allclose(lp.cpu().numpy(), rl, rtol=1e-11, atol=1e-11), name
+        assert np.allclose(g.cpu().numpy(), rg, rtol=1e-10, atol=1e-10), name
+        l1, g1 = m.log_density_gradient(th[0])           # NumPy vector in, float / ndarray out
+        assert isinstance(l1, float) and np.isclose(l1, rl[0]) and g1.shape == (m.dim(),)
+        assert np.isclose(m.log_density(th[0]), rl[0])
+    f = kb.BSModel(stan_file="stan/funnel.stan", data={"D": 1}, device=device())
+    lp, g = f.log_density_gradient(np.array([-2000.0, 1.0]))    # overflow -> -inf / zeros (bsmodel.py:15-30)
+    assert lp == -np.inf and np.all(g == 0)
+
+
+def test_outer_accumulate():
+    rng = np.random.default_rng(1)
+    for B, D in ((1000, 7), (5000, 100), (33, 40)):
+        x = rng.normal(size=(B, D))
+        sh = rng.normal(size=D)
+        outer = torch.zeros(D, D, dtype=torch.float64, device=device())
+        s1 = torch.zeros(D, dtype=torch.float64, device=device())
+        kb.outer_accumulate(up(x), up(sh), outer, s1)
+        torch.cuda.synchronize()
+        assert np.allclose(outer.cpu().numpy(), (x - sh).T @ (x - sh), rtol=1e-11, atol=1e-9)
+        assert np.allclose(s1.cpu().numpy(), (x - sh).sum(0), rtol=1e-11, atol=1e-9)

@@ -1,0 +1,136 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/klhr_sm100.h
+declares (no compute calls), host adaptation logic, world_size-2 gloo reduction."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    from klhr_b200 import _lib
+    if not _lib.LIB_PATH.exists():
+        g.build()
+    header = (ROOT / "include" / "klhr_sm100.h").read_text()
+    declared = set(re.findall(r"^(?:int|size_t)\s+(klhr_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.EXPORTS), (declared, set(_lib.EXPORTS))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.klhr_abi_version() == 1
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.klhr_model_eval(None, 0, None, None, None, 0, None) < 0
+    assert "model is NULL" in _lib.last_error()
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors must have the C sizes (checked by compiling a probe with gcc)."""
+    import ctypes as C
+    from klhr_b200 import _lib
+    src = '#include <stdio.h>\n#include "klhr_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(klhr_model_t),sizeof(klhr_fit_t),sizeof(klhr_direction_t),sizeof(klhr_trace_t),' \
+          'sizeof(klhr_accum_t));return 0;}'
+    exe = ROOT / "build" / "abi_probe"
+    exe.parent.mkdir(exist_ok=True)
+    (exe.parent / "abi_probe.c").write_text(src)
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(exe.parent / "abi_probe.c"), "-o", str(exe)], check=True)
+    sizes = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
+    mine = [C.sizeof(t) for t in (_lib.ModelDesc, _lib.FitDesc, _lib.DirectionDesc, _lib.TraceDesc, _lib.AccumDesc)]
+    assert sizes == mine
+
+
+def test_windowed_adaptation_matches_reference_schedule():
+    from klhr_b200.adaptation import WindowedAdaptation
+    from oracle.adapt import window_closures
+    assert WindowedAdaptation(1000, 50, 2).closures == [50, 150, 350, 1000]
+    for warm in (0, 10, 49, 51, 100, 101, 777, 1000, 15000):
+        for ws in (5, 25, 50):
+            if warm == ws:
+                continue
+            assert WindowedAdaptation(warm, ws, 2).closures == window_closures(warm, ws, 2)
+    wa = WindowedAdaptation(100, 50, 2)
+    assert [m for m in range(1, 300) if wa.window_closed(m)] == [50, 100]
+    assert wa.next_closure(0) == 50 and wa.next_closure(50) == 100 and wa.next_closure(100) is None
+
+
+def test_pooled_moments_and_pca_against_oracle():
+    from klhr_b200.adaptation import OnlineMoments, OnlinePCA
+    from oracle import adapt
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(600, 5)) * [1, 2, 3, 4, 5] + 3
+    om = OnlineMoments(5, shift=torch.as_tensor(X[0]))
+    for blk in np.array_split(X, 7):
+        om.update(blk)
+    rm = adapt.RunningMoments(5)
+    for x in X:
+        rm.update(x)
+    assert np.allclose(om.mean().numpy(), rm.mean(), rtol=1e-12)
+    assert np.allclose(om.var().numpy(), rm.var(), rtol=1e-10)
+    assert torch.all(OnlineMoments(5).var() == 1)                     # N <= 2 -> ones (onlinemoments.py:20-23)
+    pca = OnlinePCA(5, K=2)
+    U = X - X.mean(0)
+    pca.update(U)
+    w, V = np.linalg.eigh(U.T @ U / len(U))
+    assert np.allclose(pca.values(), w[::-1][:2] + 1e-10)
+    assert np.allclose(np.abs(pca.vectors().T @ V[:, ::-1][:, :2]), np.eye(2), atol=1e-9)
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from klhr_b200.adaptation import OnlineMoments, OnlinePCA, allreduce_adaptation
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)
+    X = rng.normal(size=(400, 6)) @ rng.normal(size=(6, 6))
+    mine = np.array_split(X, world)[rank]                             # chains sharded over ranks
+    mom, gmom, pca = OnlineMoments(6), OnlineMoments(6), OnlinePCA(6, K=2)
+    mom.update(mine)
+    gmom.update(-mine)
+    pca.update(mine)
+    allreduce_adaptation([mom, gmom], pca)
+    res = dict(N=mom.N, n=pca.n, mean=mom.mean().numpy(), var=mom.var().numpy(), gvar=gmom.var().numpy(),
+               vals=pca.values(), vecs=pca.vectors())
+    torch.save(res, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_window_closure_allreduce_world_size_2_gloo(tmp_path):
+    """The only collective of the sampler: raw pooled sums all-reduced at a window closure give
+    every rank the single-process answer."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0", weights_only=False), torch.load(out + ".1", weights_only=False)
+    rng = np.random.default_rng(123)
+    X = rng.normal(size=(400, 6)) @ rng.normal(size=(6, 6))
+    assert r0["N"] == r1["N"] == 400 and r0["n"] == 400
+    for k in ("mean", "var", "gvar", "vals", "vecs"):
+        assert np.array_equal(r0[k], r1[k])                            # bit-identical on every rank
+    assert np.allclose(r0["mean"], X.mean(0)) and np.allclose(r0["var"], X.var(0, ddof=1))
+    w, V = np.linalg.eigh(X.T @ X / 400)
+    assert np.allclose(r0["vals"], w[::-1][:2] + 1e-10)
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "klhr_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_fit_config_validation():
+    import klhr_b200 as kb
+    with pytest.raises(ValueError):
+        kb.FitConfig(family="laplace")
+    with pytest.raises(ValueError):
+        kb.FitConfig(N=64)
+    f = kb.FitConfig()
+    assert np.isclose(f.w.sum(), 1) and f.descriptor().n_nodes == 8
+    assert kb.FitConfig().for_dtype(torch.float32).gtol2 >= 1e-5
