@@ -41,7 +41,7 @@ SEED = 20261018
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=65_536, help="chains per GPU")
@@ -147,7 +147,7 @@ def run_reference(args):
 
 # =============================================================================== clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -156,12 +156,15 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and active throttle reasons over samples inside [t_begin, t_end]
+        (time.time() stamps of the timed region); all samples if the window holds none."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -176,6 +179,15 @@ class ClockSampler:
         sm, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         mx = None
+        def stamp(s):
+            try:
+                return datetime.datetime.strptime(s.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                return None
+        if t_begin is not None:
+            inside = [r for r in rows if (stamp(r[0]) or 0) >= t_begin - 0.05 and (stamp(r[0]) or 0) <= t_end + 0.05]
+            out["samples_total"] = len(rows)
+            rows = inside or rows
         for r in rows:
             try:
                 sm.append(float(r[1]))
@@ -227,14 +239,15 @@ def run_b200(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     # ---------------------------------------------------------------- resident arm
+    clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~0.5 s to spin up
     for _ in range(W):
         sampler.run(S)
     torch.cuda.synchronize()
-    clocks = ClockSampler(local) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    wall0 = time.time()
     for k in range(K):
         flush.zero_()                          # L2 flush between timed iterations (state is 52 MB < L2)
         evs[k][0].record()
@@ -248,7 +261,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     total_ms = float(dev_ms.item())
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(wall0, time.time()) if clocks else None
     value = world * B * S * K / (total_ms * 1e-3)
 
     # ---------------------------------------------------------------- end-to-end arm (host buffers)

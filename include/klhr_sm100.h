@@ -53,6 +53,9 @@ typedef struct klhr_model {
 } klhr_model_t;
 
 #define KLHR_MAX_NODES 32
+/* klhr_fit_t.flags: run the general octet-per-chain kernel even where the faster tile kernel
+ * (diagonal-Gaussian targets, Gaussian family) applies -- used by the parity tests to cover both */
+#define KLHR_FIT_FORCE_OCTET 1
 
 /* Line-fit configuration: the reference's constructor arguments that reach the fit
  * (klhr.py:16-49 / klhr_sinh.py:15-47) plus the fixed iteration budget that replaces
@@ -61,7 +64,7 @@ typedef struct klhr_fit {
     int32_t family;              /* KLHR_FAMILY_*                                          */
     int32_t n_nodes;             /* N, Gauss-Hermite nodes (<= KLHR_MAX_NODES)            */
     int32_t n1, n2, nb;          /* stage-1 iterations, stage-2 Newton steps, halvings    */
-    int32_t reserved;
+    int32_t flags;               /* KLHR_FIT_* bits                                        */
     double initscale;            /* klhr.py:24                                            */
     double tol;                  /* klhr.py:28 / klhr_sinh.py:26                          */
     double scale_clip;           /* klhr.py:30 / klhr_sinh.py:28                          */

@@ -6,7 +6,7 @@
 #include <cmath>
 #include <string>
 
-#include "klhr_step.cuh"
+#include "klhr_tile.cuh"
 
 namespace klhr {
 
@@ -74,8 +74,16 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     return 0;
 }
 
+// The tile kernel covers: diagonal-Gaussian targets, Gaussian family, no in-kernel accumulators
+// and no thinned-draw output.  Everything else runs on the general octet kernel.
+static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
+    return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && !a.acc.draws &&
+           (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && a.fp.N <= kMaxNodes;
+}
+
 static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, bool accum, cudaStream_t st,
-                         LaunchInfo* info) {
+                         LaunchInfo* info, int flags) {
+    if (tile_applies(a, family, accum, flags)) return launch_tile(a, dtype, replay, st, info);
     switch (a.mp.id) {
         case KLHR_MODEL_NORMAL: return launch_step_normal(a, dtype, family, replay, accum, st, info);
         case KLHR_MODEL_ILL_NORMAL: return launch_step_ill_normal(a, dtype, family, replay, accum, st, info);
@@ -159,8 +167,9 @@ int klhr_model_eval(const klhr_model_t* model, int dtype, const void* theta_dev,
     ModelParams mp;
     if (int e = check_model(model, mp)) return e;
     if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
-    if (!theta_dev || !lp_dev) return fail(-1, "theta and lp must not be NULL");
     if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    if (n_chains == 0) return 0;
+    if (!theta_dev || !lp_dev) return fail(-1, "theta and lp must not be NULL");
     cudaStream_t st = (cudaStream_t)stream;
     int e = -2;
     switch (mp.id) {
@@ -183,6 +192,7 @@ int klhr_step_replay(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     if (int e = check_model(model, a.mp)) return e;
     if (int e = check_fit(fit, a.fp)) return e;
     if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains == 0) return 0;
     if (!theta_dev || !rho_dev || !z_init_dev || !z_prop_dev || !u_dev)
         return fail(-1, "theta, rho, z_init, z_prop, u must not be NULL");
     if (fit->family == KLHR_FAMILY_SINH && !init4_dev) return fail(-1, "sinh family needs init4");
@@ -193,7 +203,7 @@ int klhr_step_replay(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     a.acc.thin = 1;
     if (trace) a.tr = *trace;
     a.tr.z_init = a.tr.z_prop = a.tr.u = a.tr.init4 = nullptr;   // inputs in this mode
-    return cuda_fail(dispatch_step(a, dtype, fit->family, true, false, (cudaStream_t)stream, nullptr),
+    return cuda_fail(dispatch_step(a, dtype, fit->family, true, false, (cudaStream_t)stream, nullptr, fit->flags),
                      "klhr_step_replay");
 }
 
@@ -233,12 +243,13 @@ int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direct
     StepArgs a;
     bool use_acc;
     if (int e = fill_run(a, model, fit, dir, dtype, n_chains, accum, trace, use_acc)) return e;
-    if (!theta_dev) return fail(-1, "theta must not be NULL");
     if (n_steps < 0 || chain_offset < 0 || draw_offset < 0) return fail(-10, "negative count or offset");
-    if (n_steps == 0) return 0;
+    if (n_steps == 0 || n_chains == 0) return 0;
+    if (!theta_dev) return fail(-1, "theta must not be NULL");
     a.theta = theta_dev;
     a.chain_offset = chain_offset; a.draw_offset = draw_offset; a.n_steps = n_steps; a.seed = seed;
-    return cuda_fail(dispatch_step(a, dtype, fit->family, false, use_acc, (cudaStream_t)stream, nullptr), "klhr_run");
+    return cuda_fail(dispatch_step(a, dtype, fit->family, false, use_acc, (cudaStream_t)stream, nullptr, fit->flags),
+                     "klhr_run");
 }
 
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running, int accumulate,
@@ -250,7 +261,7 @@ int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
     a.acc.thin = 1;
     LaunchInfo li;
-    const int e = dispatch_step(a, dtype, fit->family, !free_running, accumulate != 0, nullptr, &li);
+    const int e = dispatch_step(a, dtype, fit->family, !free_running, accumulate != 0, nullptr, &li, fit->flags);
     if (e) return cuda_fail(e, "klhr_launch_info") > 0 ? -30 : e;
     if (threads_per_cta) *threads_per_cta = li.threads;
     if (smem_bytes) *smem_bytes = li.smem;

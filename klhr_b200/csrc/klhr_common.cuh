@@ -103,6 +103,30 @@ struct Philox {
         }
         out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
     }
+    // Four blocks whose counters differ only in c3 = slot0 + stride * b, advanced round by round
+    // so that the 8 independent multiplies per round overlap (one block alone is a serial chain).
+    __device__ static __forceinline__ void block4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t slot0,
+                                                   uint32_t stride, uint32_t k0, uint32_t k1, uint32_t out[4][4]) {
+        uint32_t s[4][4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { s[b][0] = c0; s[b][1] = c1; s[b][2] = c2; s[b][3] = slot0 + stride * b; }
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint64_t p0 = (uint64_t)M0 * s[b][0];
+                const uint64_t p1 = (uint64_t)M1 * s[b][2];
+                const uint32_t n0 = (uint32_t)(p1 >> 32) ^ s[b][1] ^ k0;
+                const uint32_t n2 = (uint32_t)(p0 >> 32) ^ s[b][3] ^ k1;
+                s[b][0] = n0; s[b][1] = (uint32_t)p1; s[b][2] = n2; s[b][3] = (uint32_t)p0;
+            }
+            k0 += W0; k1 += W1;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[b][q] = s[b][q];
+    }
 };
 
 // slots of one (chain, draw) stream
@@ -110,7 +134,7 @@ constexpr uint32_t kSlotScalarA = 0;   // w0: direction-column uniform; w2,w3: z
 constexpr uint32_t kSlotProposal = 1;  // w0..w3: two 53-bit uniforms -> Box-Muller -> z_prop
 constexpr uint32_t kSlotAccept = 2;    // w0,w1: 53-bit accept uniform
 constexpr uint32_t kSlotInit4 = 3;     // w0..w3: two Box-Muller pairs -> init4[2], init4[3] (sinh)
-constexpr uint32_t kSlotDir = 8;       // + lane + 8*q : 4 direction normals per block
+constexpr uint32_t kSlotDir = 8;       // element i of the direction: slot kSlotDir + (i % 32) + 32 (i / 128), word (i / 32) % 4
 
 // uniform in (0,1) from 32 bits: (x + 0.5) / 2^32
 __device__ __forceinline__ float u01_32(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
@@ -124,12 +148,13 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
 // random direction law (any rho is a valid hit-and-run direction), not 1-ulp accurate.
 __device__ __forceinline__ void box_muller_f32(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u = u01_32(a);
-    const float v = u01_32(b);
-    const float rad = sqrtf(-2.0f * __logf(u));
-    float s, c;
-    __sincosf(6.283185307179586f * v, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+    // -2 ln u = (-2 ln 2) lg2 u ; MUFU.LG2, MUFU.SQRT, MUFU.SIN/COS (approximate units are fine
+    // for a direction law; the proposal normal uses box_muller_f64)
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u)));
+    const float ang = (float)b * 1.4629180792671596e-09f;       // 2 pi / 2^32 * b
+    z0 = rad * __cosf(ang);
+    z1 = rad * __sinf(ang);
 }
 
 __device__ __forceinline__ void box_muller_f64(double u, double v, double& z0, double& z1) {

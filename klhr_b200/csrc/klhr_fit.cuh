@@ -3,8 +3,13 @@
 // Newton iteration, and the Metropolis-Hastings pieces (klhr.py:155-158,175-190,
 // klhr_sinh.py:112-114,233-260).  Mirrors oracle/batched.py operation for operation.
 //
-// All functions are called by the 8 lanes of an octet together; every scalar they return
-// is uniform across the octet.  Lane n owns quadrature node n (n, n+8, .. for N > 8).
+// Every function is templated on the group size G that cooperates on ONE chain:
+//   G = 8  the 8 lanes of an octet call together; lane n owns quadrature node n (n, n+8, ..)
+//          and back-tracking candidate n; sums are 3-level xor-shuffles; results are uniform
+//          across the octet (klhr_step.cuh);
+//   G = 1  a single thread owns the chain and loops over nodes / candidates itself, no
+//          shuffles (klhr_tile.cuh, thread-per-chain fit).
+// Both produce the same iterates up to the summation order of the quadrature sums.
 #pragma once
 #include "klhr_common.cuh"
 
@@ -26,8 +31,14 @@ struct FitResult {
     bool converged;
 };
 
+template <int G, typename R>
+__device__ __forceinline__ R grp_sum(R v, unsigned m) {
+    if constexpr (G == kOct) return oct_sum(v, m);
+    else return v;
+}
+
 // ------------------------------------------------------------------ stage 1: 1-D mode search
-template <typename R, typename Model>
+template <int G, typename R, typename Model>
 __device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitParams& fp, int lane,
                             unsigned m, R& xi_out, R& tau0_out, int& nev) {
     R xi = z_init * (R)fp.initscale;
@@ -35,40 +46,57 @@ __device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitP
     bool done = false;
     Jet<R> J = Model::eval(cf, xi);
     nev = 1;
-    const R ks = (R)1 / (R)(1 << lane);
+    const R gt1sq = (R)fp.gtol1 * (R)fp.gtol1;
     for (int it = 0; it < fp.n1; ++it) {
         const bool concave = J.l2 < R(0);
-        const R sc = concave ? R(1) / r_sqrt(-J.l2) : R(1);
-        const bool conv = concave && (r_abs(J.l1) * sc <= (R)fp.gtol1);
+        // |l'| / sqrt(-l'') <= gtol1, written without the square root and the division
+        const bool conv = concave && (J.l1 * J.l1 <= gt1sq * (-J.l2));
         done = done || conv || !r_finite(J.l);
         if (done) break;
         const R newton = concave ? -J.l1 / J.l2 : R(0);
         const R step = concave ? r_clamp(newton, -R(8) * trust, R(8) * trust) : r_clamp(J.l1, -trust, trust);
-        const R cand = xi + step * ks;
-        const Jet<R> C = Model::eval(cf, cand);
         nev += kOct;
-        // arg-max of C.l over the octet, first maximum on ties
-        R bv = C.l;
-        int bi = lane;
+        // the 8 candidates xi + 2^-k step: keep the arg-max of l, first maximum on ties
+        R bv, bx, b1, b2;
+        int bi;
+        if constexpr (G == kOct) {
+            const R cand = xi + step * ((R)1 / (R)(1 << lane));
+            const Jet<R> C = Model::eval(cf, cand);
+            bv = C.l;
+            bi = lane;
 #pragma unroll
-        for (int off = 1; off < kOct; off <<= 1) {
-            const R ov = __shfl_xor_sync(m, bv, off);
-            const int oi = __shfl_xor_sync(m, bi, off);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            for (int off = 1; off < kOct; off <<= 1) {
+                const R ov = __shfl_xor_sync(m, bv, off);
+                const int oi = __shfl_xor_sync(m, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            bx = oct_bcast(cand, bi, m);
+            b1 = oct_bcast(C.l1, bi, m);
+            b2 = oct_bcast(C.l2, bi, m);
+        } else {
+            bv = -Num<R>::inf(); bi = 0; bx = xi; b1 = 0; b2 = 0;
+            R ks = 1;
+#pragma unroll
+            for (int k = 0; k < kOct; ++k) {
+                const R cand = xi + step * ks;
+                const Jet<R> C = Model::eval(cf, cand);
+                if (C.l > bv) { bv = C.l; bi = k; bx = cand; b1 = C.l1; b2 = C.l2; }
+                ks *= R(0.5);
+            }
         }
         const bool improve = bv > J.l;
         const bool full = improve && bi == 0;
         if (improve) {
-            xi = oct_bcast(cand, bi, m);
+            xi = bx;
             J.l = bv;
-            J.l1 = oct_bcast(C.l1, bi, m);
-            J.l2 = oct_bcast(C.l2, bi, m);
+            J.l1 = b1;
+            J.l2 = b2;
         }
         trust = full ? trust * R(2) : (improve ? trust : trust * R(1.0 / 256.0));
         done = done || (!improve && (r_abs(step) * R(1.0 / 128.0) <= Num<R>::eps * (R(1) + r_abs(xi))));
     }
     xi_out = xi;
-    tau0_out = (J.l2 < R(0)) ? R(0.5) * r_log(-R(1) / J.l2) : R(0);
+    tau0_out = (J.l2 < R(0)) ? -R(0.5) * r_log(-J.l2) : R(0);
 }
 
 // ------------------------------------------------------------------ small dense algebra
@@ -160,13 +188,13 @@ __device__ __forceinline__ void newton_direction(const KLState<R, n>& S, const F
 
 // ------------------------------------------------------------------ KL objective, Gaussian family
 // reference klhr.py:106-120 in scaled coordinates (m/s, tau); Hessian from l''.
-template <typename R, typename Model>
+template <int G, typename R, typename Model>
 __device__ void kl_gauss(const typename Model::Coef& cf, const R (&eta)[2], const FitParams& fp, int lane,
                          unsigned m, KLState<R, 2>& S) {
     const R clip = (R)fp.scale_clip;
     const R s = r_exp(r_clamp(eta[1], -clip, clip));
     R S0 = 0, S1 = 0, S1x = 0, S2 = 0, S2x = 0, S2xx = 0;
-    for (int n = lane; n < fp.N; n += kOct) {
+    for (int n = lane; n < fp.N; n += G) {
         const R x = (R)fp.x[n], w = (R)fp.w[n];
         const R y = s * x + eta[0];
         const Jet<R> J = Model::eval(cf, y);
@@ -179,8 +207,8 @@ __device__ void kl_gauss(const typename Model::Coef& cf, const R (&eta)[2], cons
         S2x += w2 * x;
         S2xx += w2 * x * x;
     }
-    S0 = oct_sum(S0, m); S1 = oct_sum(S1, m); S1x = oct_sum(S1x, m);
-    S2 = oct_sum(S2, m); S2x = oct_sum(S2x, m); S2xx = oct_sum(S2xx, m);
+    S0 = grp_sum<G>(S0, m); S1 = grp_sum<G>(S1, m); S1x = grp_sum<G>(S1x, m);
+    S2 = grp_sum<G>(S2, m); S2x = grp_sum<G>(S2x, m); S2xx = grp_sum<G>(S2xx, m);
     const R s2 = s * s;
     S.f = -(S0 + eta[1]);
     S.g[0] = -S1 * s;
@@ -207,7 +235,7 @@ __device__ __forceinline__ SinhPar<R> sinh_unpack(const R (&eta)[4], const FitPa
 
 // reference klhr_sinh.py:163-176; gradients are _grad_T (:116-124) and _grad_log_abs_jac
 // (:146-156); second derivatives are those expressions differentiated once more.
-template <typename R, typename Model>
+template <int G, typename R, typename Model>
 __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const FitParams& fp, int lane,
                         unsigned m, KLState<R, 4>& S) {
     const SinhPar<R> q = sinh_unpack<R>(eta, fp);
@@ -215,7 +243,7 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
     const R invd = R(1) / q.d;
     R f = 0, g1 = 0, g2 = 0, g3 = 0, g0 = 0;
     R h00 = 0, h01 = 0, h02 = 0, h03 = 0, h11 = 0, h12 = 0, h13 = 0, h22 = 0, h23 = 0, h33 = 0;
-    for (int n = lane; n < fp.N; n += kOct) {
+    for (int n = lane; n < fp.N; n += G) {
         const R w = (R)fp.w[n];
         const R a = ((R)fp.cx[n] + q.e) * invd;
         const R ac = r_clamp(a, -c, c);
@@ -249,11 +277,11 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         h23 += w * (L23 - J.l2 * t2 * t3 - J.l1 * T23);
         h33 += w * (L33 - J.l2 * t3 * t3 - J.l1 * T33);
     }
-    S.f = oct_sum(f, m);
-    g0 = oct_sum(g0, m); g1 = oct_sum(g1, m); g2 = oct_sum(g2, m); g3 = oct_sum(g3, m);
-    h00 = oct_sum(h00, m); h01 = oct_sum(h01, m); h02 = oct_sum(h02, m); h03 = oct_sum(h03, m);
-    h11 = oct_sum(h11, m); h12 = oct_sum(h12, m); h13 = oct_sum(h13, m);
-    h22 = oct_sum(h22, m); h23 = oct_sum(h23, m); h33 = oct_sum(h33, m);
+    S.f = grp_sum<G>(f, m);
+    g0 = grp_sum<G>(g0, m); g1 = grp_sum<G>(g1, m); g2 = grp_sum<G>(g2, m); g3 = grp_sum<G>(g3, m);
+    h00 = grp_sum<G>(h00, m); h01 = grp_sum<G>(h01, m); h02 = grp_sum<G>(h02, m); h03 = grp_sum<G>(h03, m);
+    h11 = grp_sum<G>(h11, m); h12 = grp_sum<G>(h12, m); h13 = grp_sum<G>(h13, m);
+    h22 = grp_sum<G>(h22, m); h23 = grp_sum<G>(h23, m); h33 = grp_sum<G>(h33, m);
     const R s = q.s;
     S.g[0] = g0 * s; S.g[1] = g1; S.g[2] = g2; S.g[3] = g3;
     S.H[0][0] = h00 * s * s;
@@ -264,11 +292,11 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
     S.H[2][2] = h22; S.H[2][3] = S.H[3][2] = h23; S.H[3][3] = h33;
 }
 
-template <typename R, typename Model, int n>
+template <int G, typename R, typename Model, int n>
 __device__ __forceinline__ void kl_eval(const typename Model::Coef& cf, const R (&eta)[n], const FitParams& fp,
                                         int lane, unsigned m, KLState<R, n>& S) {
-    if constexpr (n == 2) kl_gauss<R, Model>(cf, eta, fp, lane, m, S);
-    else kl_sinh<R, Model>(cf, eta, fp, lane, m, S);
+    if constexpr (n == 2) kl_gauss<G, R, Model>(cf, eta, fp, lane, m, S);
+    else kl_sinh<G, R, Model>(cf, eta, fp, lane, m, S);
 }
 
 template <typename R, int n>
@@ -279,11 +307,11 @@ __device__ __forceinline__ R scale_of(const R (&eta)[n], const FitParams& fp) {
 }
 
 // ------------------------------------------------------------------ stage 2: damped Newton on KL
-template <typename R, typename Model, int n>
+template <int G, typename R, typename Model, int n>
 __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
                               unsigned m, int& nev, bool& converged) {
     KLState<R, n> S;
-    kl_eval<R, Model, n>(cf, eta, fp, lane, m, S);
+    kl_eval<G, R, Model, n>(cf, eta, fp, lane, m, S);
     nev = 1;
     bool conv = false;
     for (int it = 0; it < fp.n2; ++it) {
@@ -311,7 +339,7 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
 #pragma unroll
             for (int i = 1; i < n; ++i) trial[i] = eta[i] + t * p[i];
             KLState<R, n> St;
-            kl_eval<R, Model, n>(cf, trial, fp, lane, m, St);
+            kl_eval<G, R, Model, n>(cf, trial, fp, lane, m, St);
             nev += 1;
             const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S.f));
             const bool ok = r_finite(St.f) &&
@@ -377,12 +405,12 @@ struct StepOut {
 
 // z_init, init2/init3 (sinh start for log d, e), z_prop, u are the step's variates
 // (reference draw order: klhr.py:129,180,188 ; klhr_sinh.py:184,191,246,255).
-template <typename R, typename Model, int n>
+template <int G, typename R, typename Model, int n>
 __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams& fp, int lane, unsigned m,
                                 R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o) {
     R xi, tau0;
     int nev1, nev2;
-    stage1_mode<R, Model>(cf, z_init, fp, lane, m, xi, tau0, nev1);
+    stage1_mode<G, R, Model>(cf, z_init, fp, lane, m, xi, tau0, nev1);
     R eta[n];
     eta[0] = xi;
     eta[1] = tau0;
@@ -391,14 +419,17 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
         eta[3] = init3 * (R)fp.initscale;
     }
     bool conv;
-    stage2_newton<R, Model, n>(cf, eta, fp, lane, m, nev2, conv);
+    stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv);
     R zp, lq0, lq1;
     if constexpr (n == 2) {
         const R c = (R)fp.scale_clip;
         const R s = r_exp(r_clamp(eta[1], -c, c));
         zp = eta[0] + s * z_prop;                   // klhr.py:180
-        lq0 = logq_gauss<R>(R(0), eta, fp);
-        lq1 = logq_gauss<R>(zp, eta, fp);
+        // _logq(0) - _logq(zp) (klhr.py:155-158,185-186): the two -log(s) terms cancel, so only
+        // the quadratic parts are formed (saves two logs and two exps per draw)
+        const R z0 = (R(0) - eta[0]) / s, z1 = (zp - eta[0]) / s;
+        lq0 = -R(0.5) * z0 * z0;
+        lq1 = -R(0.5) * z1 * z1;
     } else {
         zp = transport_sinh<R>(z_prop, eta, fp);    // klhr_sinh.py:246
         lq0 = logq_sinh<R>(R(0), eta, fp);

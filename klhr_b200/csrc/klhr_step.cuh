@@ -18,6 +18,9 @@
 namespace klhr {
 
 constexpr int kThreadsMax = 256;
+#ifndef KLHR_MIN_CTAS
+#define KLHR_MIN_CTAS 2
+#endif
 
 struct StepArgs {
     ModelParams mp;
@@ -54,7 +57,7 @@ __host__ __device__ inline int pad_dim(int D, int real_bytes) {
 }
 
 template <typename R, typename Model, int NE, bool kReplay, bool kAccum>
-__global__ void __launch_bounds__(kThreadsMax) step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.mp.D;
     const int Dpad = a.Dpad;
@@ -169,20 +172,24 @@ __global__ void __launch_bounds__(kThreadsMax) step_kernel(const __grid_constant
                     mcol = s_mean + (size_t)j * D;
                 }
                 R ss = 0;
-                for (int base = 0; base < D; base += 4 * kOct) {
-                    uint32_t w[4];
-                    Philox::block(c0, c1, d0, kSlotDir + (uint32_t)lane + (uint32_t)(base / 4), k0, k1d, w);
-                    float z[4];
-                    box_muller_f32(w[0], w[1], z[0], z[1]);
-                    box_muller_f32(w[2], w[3], z[2], z[3]);
+                // element i = g0 + lane + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128),
+                // word r; x is formed in fp32 (same stream and rounding as the tile kernel)
+                for (int g0 = 0; g0 < D; g0 += 128) {
+                    for (int t = 0; t < 4 && g0 + 8 * t < D; ++t) {
+                        uint32_t w[4];
+                        Philox::block(c0, c1, d0, kSlotDir + (uint32_t)(lane + 8 * t) + (uint32_t)(g0 / 4), k0, k1d, w);
+                        float z[4];
+                        box_muller_f32(w[0], w[1], z[0], z[1]);
+                        box_muller_f32(w[2], w[3], z[2], z[3]);
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int i = base + rr * kOct + lane;
-                        if (i < D) {
-                            const R x = (mcol ? mcol[i] : R(0)) + s_sd[i] * (R)z[rr];
-                            rh[i] = x;
-                            const R xt = x + tol;
-                            ss += xt * xt;
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int i = g0 + lane + 8 * t + 32 * rr;
+                            if (i < D) {
+                                const R x = (R)fmaf((float)s_sd[i], z[rr], mcol ? (float)mcol[i] : 0.0f);
+                                rh[i] = x;
+                                const R xt = x + tol;
+                                ss += xt * xt;
+                            }
                         }
                     }
                 }
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(kThreadsMax) step_kernel(const __grid_constant
             const typename Model::Coef cf = Model::setup(th, rh, lane, om, a.mp);
             // ---------------------------------------------------------------- 3.+4. fit, propose, MH
             StepOut<R> so;
-            fit_and_propose<R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so);
+            fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so);
             if (so.accept) {
                 for (int i = lane; i < D; i += kOct) th[i] = th[i] + so.zp * rh[i];
                 ++n_acc;

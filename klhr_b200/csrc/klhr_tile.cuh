@@ -1,0 +1,279 @@
+// klhr_b200 -- the TILE kernel: the fast path for diagonal-Gaussian targets
+// (stan/normal.stan, stan/ill-normal.stan) with the Gaussian line family.
+//
+// One warp owns a tile of 32 chains and alternates between two shapes per draw:
+//   D-phase   8 passes; in pass p the 4 octets of the warp each process ONE chain (slot 4p+o)
+//             cooperatively: theta row streamed from global memory (L2-resident between
+//             draws), the pending update of the previous draw applied on the fly
+//             (theta += c * x_prev, written back only if the draw was accepted), Philox ->
+//             Box-Muller -> x = mean + sd z kept as fp32 in shared memory, and the three sums
+//             ||x+tol||^2, sum x^2 w, sum x theta w reduced with 3-level octet shuffles;
+//   fit-phase thread-per-chain: lane 8o+j owns chain slot 4j+o, turns the sums into the line
+//             coefficients (A, Bq) of klhr_models.cuh:QuadCoef and runs stage 1 / stage 2 /
+//             proposal / MH of klhr_fit.cuh with G = 1 -- no shuffles, no redundant lanes.
+// Compared with the octet kernel (klhr_step.cuh) the per-chain scalar work is done once
+// instead of eight times and theta is read once and written at most once per draw.
+//
+// Variate streams are the same function of (seed, chain, draw, element) as in the octet
+// kernel, so both kernels produce the same chains up to fp32 rounding of the direction.
+#pragma once
+#include "klhr_step.cuh"
+
+namespace klhr {
+
+constexpr int kTileChains = 32;
+
+// per-draw scalar variates of one chain (slots 0..2), computed by the owning thread
+template <typename R>
+__device__ __forceinline__ void chain_scalars(uint32_t c0, uint32_t c1, uint32_t d0, uint32_t k0, uint32_t k1d,
+                                              R& u_col, R& z_init, R& z_prop, R& u) {
+    uint32_t w[4];
+    Philox::block(c0, c1, d0, kSlotScalarA, k0, k1d, w);
+    float f0, f1;
+    box_muller_f32(w[2], w[3], f0, f1);
+    u_col = (R)u01_32(w[0]);
+    z_init = (R)f0;
+    Philox::block(c0, c1, d0, kSlotProposal, k0, k1d, w);
+    if (sizeof(R) == 8) {
+        double z0, z1;
+        box_muller_f64(u01_53(w[0], w[1]), u01_53(w[2], w[3]), z0, z1);
+        z_prop = (R)z0;
+    } else {
+        box_muller_f32(w[0], w[2], f0, f1);
+        z_prop = (R)f0;
+    }
+    Philox::block(c0, c1, d0, kSlotAccept, k0, k1d, w);
+    u = sizeof(R) == 8 ? (R)u01_53(w[0], w[1]) : (R)u01_32(w[0]);
+}
+
+template <typename R, bool kScaled, typename XT, bool kReplay>
+__global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_constant__ StepArgs a) {
+    using Model = DiagNormal<R, kScaled>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.mp.D;
+    const int Dx = a.Dpad;                               // row stride of xs
+    const int L = threadIdx.x;
+    const int o = L >> 3, j = L & 7;
+    const unsigned om = oct_mask();
+    XT* xs = reinterpret_cast<XT*>(smem_raw);            // [32][Dx]
+    float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);   // [D]
+    float* s_mean = s_sd + D;                            // [n_cols][D]
+    const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+
+    const long long tile0 = (long long)blockIdx.x * kTileChains;
+    const long long c_own = tile0 + 4 * j + o;           // the chain this thread owns in the fit phase
+    const bool own_valid = c_own < a.B;
+    R* g_theta = reinterpret_cast<R*>(a.theta);
+    const R* g_w = reinterpret_cast<const R*>(a.mp.p0);
+
+    if constexpr (!kReplay) {
+        const R* g_sd = reinterpret_cast<const R*>(a.dir.sd);
+        const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
+        for (int i = L; i < D; i += kTileChains) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
+        for (int i = L; i < n_cols * D; i += kTileChains) s_mean[i] = (float)g_mean[i];
+        __syncwarp();
+    }
+
+    const R tol = (R)a.fp.tol;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    R c_pend = 0;                                        // zp / ||x+tol|| of the last accepted draw, else 0
+    long long n_acc = 0;
+    unsigned long long n_evals = 0;
+
+    for (int step = 0; step <= a.n_steps; ++step) {
+        const bool last = step == a.n_steps;             // extra pass: only flush pending updates
+        const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
+        const uint32_t d0 = (uint32_t)draw, k1d = k1 ^ (uint32_t)(draw >> 32);
+        R u_col = 0, z_init = 0, z_prop = 0, u = 0;
+        int jcol = 0;
+        if (!last) {
+            if constexpr (kReplay) {
+                if (own_valid) {
+                    z_init = reinterpret_cast<const R*>(a.z_init)[c_own];
+                    z_prop = reinterpret_cast<const R*>(a.z_prop)[c_own];
+                    u = reinterpret_cast<const R*>(a.u)[c_own];
+                }
+            } else {
+                const unsigned long long cid = (unsigned long long)(a.chain_offset + c_own);
+                chain_scalars<R>((uint32_t)cid, (uint32_t)(cid >> 32), d0, k0, k1d, u_col, z_init, z_prop, u);
+                if (n_cols > 1) {
+                    const R* cdf = reinterpret_cast<const R*>(a.dir.cdf);
+                    while (jcol < n_cols - 1 && u_col >= cdf[jcol]) ++jcol;     // searchsorted 'right', klhr.py:147
+                }
+            }
+        }
+        R my_ss = 1, my_A = 0, my_B = 0;
+        // -------------------------------------------------------------------- D-phase
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int cs = 4 * p + o;
+            const long long c = tile0 + cs;
+            const R cp = oct_bcast(c_pend, p, om);
+            const int col = oct_bcast(jcol, p, om);
+            if (c >= a.B) continue;                       // octet-uniform
+            if (last && cp == R(0)) continue;
+            R* row = g_theta + c * D;
+            XT* xr = xs + (size_t)cs * Dx;
+            const float* mcol = n_cols ? s_mean + (size_t)col * D : nullptr;
+            const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
+            const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
+            R ss = 0, sA = 0, sB = 0;
+            for (int g0 = 0; g0 < D; g0 += 128) {
+                // element i = g0 + j + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128), word r
+                // 1. issue the loads of this chain's theta slice (and of the previous x when a move is
+                //    pending); nothing below depends on them until step 3, so the L2 latency hides
+                //    behind the Philox / Box-Muller arithmetic of step 2
+                R th[16];
+                XT xo[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int i = g0 + j + 8 * (s >> 2) + 32 * (s & 3);
+                    th[s] = i < D ? row[i] : R(0);
+                    xo[s] = (cp != R(0) && i < D) ? xr[i] : XT(0);
+                }
+                // 2. 16 normals: four Philox blocks advanced in lockstep, eight Box-Muller pairs
+                float z[16];
+                if constexpr (!kReplay) {
+                    if (!last) {
+                        uint32_t w[4][4];
+                        Philox::block4(c0, c1, d0, kSlotDir + (uint32_t)j + (uint32_t)(g0 / 4), 8u, k0, k1d, w);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
+                            box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
+                        }
+                    }
+                }
+                // 3. apply the pending move, form the new x and the three sums
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int i = g0 + j + 8 * (s >> 2) + 32 * (s & 3);
+                    if (i < D) {
+                        R t0 = th[s];
+                        if (cp != R(0)) {
+                            t0 = t0 + cp * (R)xo[s];
+                            row[i] = t0;
+                        }
+                        if (!last) {
+                            R x;
+                            if constexpr (kReplay) {
+                                x = reinterpret_cast<const R*>(a.rho)[c * D + i];
+                                xr[i] = (XT)x;
+                            } else {
+                                const float xf = fmaf(s_sd[i], z[s], mcol ? mcol[i] : 0.0f);
+                                xr[i] = (XT)xf;
+                                x = (R)xf;
+                            }
+                            const R xt = x + tol;
+                            ss += xt * xt;
+                            const R xw = x * Model::wgt(i, a.mp);
+                            sA += x * xw;
+                            sB += t0 * xw;
+                        }
+                    }
+                }
+            }
+            if (last) continue;
+            ss = oct_sum(ss, om);
+            sA = oct_sum(sA, om);
+            sB = oct_sum(sB, om);
+            if (j == p) { my_ss = ss; my_A = sA; my_B = sB; }
+        }
+        if (last) break;
+        // -------------------------------------------------------------------- fit phase (thread per chain)
+        R inv = 1;
+        if (own_valid) {
+            typename Model::Coef cf;
+            if constexpr (kReplay) {                      // injected rho is used as given (already normalised)
+                cf.A = my_A;
+                cf.Bq = -my_B;
+            } else {
+                inv = R(1) / r_sqrt(my_ss);               // rho = x / ||x + tol||  (klhr.py:153)
+                cf.A = my_A * inv * inv;
+                cf.Bq = -my_B * inv;
+            }
+            StepOut<R> so;
+            fit_and_propose<1, R, Model, 2>(cf, a.fp, 0, 0u, z_init, R(0), R(0), z_prop, u, so);
+            c_pend = so.accept ? so.zp * inv : R(0);
+            n_acc += so.accept ? 1 : 0;
+            n_evals += (unsigned long long)so.evals;
+            const long long trow = (long long)step * a.B + c_own;
+            if (a.tr.eta) {
+                R* e = reinterpret_cast<R*>(a.tr.eta) + trow * 2;
+                e[0] = so.eta[0];
+                e[1] = so.eta[1];
+            }
+            if (a.tr.zp) reinterpret_cast<R*>(a.tr.zp)[trow] = so.zp;
+            if (a.tr.r) reinterpret_cast<R*>(a.tr.r)[trow] = so.r;
+            if (a.tr.accept) a.tr.accept[trow] = so.accept ? 1 : 0;
+            if (a.tr.evals) a.tr.evals[trow] = so.evals;
+            if (!kReplay && a.tr.z_init) {
+                reinterpret_cast<R*>(a.tr.z_init)[trow] = z_init;
+                reinterpret_cast<R*>(a.tr.z_prop)[trow] = z_prop;
+                reinterpret_cast<R*>(a.tr.u)[trow] = u;
+            }
+        } else {
+            c_pend = 0;
+        }
+        if (a.tr.rho) {                                   // emit rho = x * inv (test / debugging path)
+            for (int p = 0; p < 8; ++p) {
+                const int cs = 4 * p + o;
+                const long long c = tile0 + cs;
+                const R ip = oct_bcast(inv, p, om);
+                if (c >= a.B) continue;
+                R* g = reinterpret_cast<R*>(a.tr.rho) + ((long long)step * a.B + c) * D;
+                for (int i = j; i < D; i += kOct) g[i] = (R)xs[(size_t)cs * Dx + i] * ip;
+            }
+        }
+        __syncwarp();
+    }
+    if (own_valid) {
+        if (a.acc.accept_count) a.acc.accept_count[c_own] += n_acc;
+    }
+    if (a.acc.evals_total) {
+        unsigned long long tot = own_valid ? n_evals : 0ull;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+        if (L == 0 && tot) atomicAdd(a.acc.evals_total, tot);
+    }
+}
+
+template <typename R, bool kScaled>
+int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, LaunchInfo* info) {
+    StepArgs a = args_in;
+    const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+    const int xbytes = replay ? (int)sizeof(R) : 4;
+    a.Dpad = pad_dim(a.mp.D, xbytes);
+    const size_t smem = (size_t)kTileChains * a.Dpad * xbytes + (size_t)(1 + n_cols) * a.mp.D * sizeof(float);
+    if (smem > 227 * 1024) return -20;
+    const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
+                            : (const void*)tile_kernel<R, kScaled, float, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    // one warp per CTA: ask for the largest shared-memory carve-out so that 14+ tiles fit per SM
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    if (info) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) return (int)e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kTileChains, smem);
+        if (e != cudaSuccess) return (int)e;
+        info->threads = kTileChains;
+        info->smem = (int)smem;
+        info->regs = fa.numRegs;
+        info->ctas_per_sm = nb;
+        return 0;
+    }
+    const long long grid = (a.B + kTileChains - 1) / kTileChains;
+    if (grid <= 0) return 0;
+    void* kargs[] = {(void*)&a};
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kTileChains), kargs, smem, st);
+    return (int)e;
+}
+
+// defined in klhr_tile.cu
+int launch_tile(const StepArgs& a, int dtype, bool replay, cudaStream_t st, LaunchInfo* info);
+
+}  // namespace klhr

@@ -44,6 +44,7 @@ class FitConfig:
     step_cap: float = 2.0
     c1: float = 1e-4
     basin: float = 1e-3
+    force_octet: bool = False          # use the general octet kernel even where the tile kernel applies
     x: np.ndarray = field(default=None, repr=False)
     w: np.ndarray = field(default=None, repr=False)
 
@@ -67,7 +68,7 @@ class FitConfig:
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin)
+                         basin=self.basin, flags=1 if self.force_octet else 0)
         for i in range(self.N):
             d.x[i] = float(self.x[i])
             d.w[i] = float(self.w[i])

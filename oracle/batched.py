@@ -121,8 +121,8 @@ def stage1_mode(model, theta, rho, z_init, cfg: FitConfig):
     for _ in range(cfg.n1):
         with np.errstate(all="ignore"):
             concave = l2 < 0
-            sc = np.where(concave, 1.0 / np.sqrt(np.where(concave, -l2, 1.0)), 1.0)
-            conv = concave & (np.abs(l1) * sc <= cfg.gtol1)
+            # |l'| / sqrt(-l'') <= gtol1 without the square root and the division
+            conv = concave & (l1 * l1 <= cfg.gtol1 * cfg.gtol1 * (-l2))
             done = done | conv | ~np.isfinite(l)
             if done.all():
                 break
@@ -145,7 +145,7 @@ def stage1_mode(model, theta, rho, z_init, cfg: FitConfig):
         # no candidate improved: shrink and retry; give up once the step is negligible
         done = done | (~improve & (np.abs(step) * (1.0 / 128.0) <= cfg.eps * (1.0 + np.abs(xi))))
     with np.errstate(all="ignore"):
-        tau0 = np.where(l2 < 0, 0.5 * np.log(np.where(l2 < 0, -1.0 / l2, 1.0)), 0.0)
+        tau0 = np.where(l2 < 0, -0.5 * np.log(np.where(l2 < 0, -l2, 1.0)), 0.0)
     return xi, tau0, nev
 
 

@@ -169,6 +169,13 @@ CASES = [
     ("rosenbrock_d4_sinh", "rosenbrock", {"D": 2}, "sinh", 1_000, dict(seed=72, overrelaxed=False), None),
     ("normal_d2_klhr_method2", "normal", {"D": 2}, "gauss", 1_500,
      dict(seed=81, eigen_method_one=False), None),
+    # long runs WITHOUT adaptation (warmup=0 -> isotropic direction law, identical on both
+    # sides): only accept flags and thinned states are kept ("stats" tapes) for the
+    # acceptance-rate and posterior parity tests.
+    ("stats_funnel_d2_klhr_noadapt", "funnel", {"D": 1}, "gauss", 30_000, dict(seed=91, warmup=0), None),
+    ("stats_funnel_d2_sinh_noadapt", "funnel", {"D": 1}, "sinh", 6_000,
+     dict(seed=92, warmup=0, overrelaxed=False), None),
+    ("stats_rosenbrock_d4_klhr_noadapt", "rosenbrock", {"D": 2}, "gauss", 20_000, dict(seed=93, warmup=0), None),
 ]
 
 
@@ -217,6 +224,10 @@ def main():
         algo = cls(model, seed=seed, **kw)
         algo.rng = TapeRNG(seed + 1000)
         tape = _tape_run(algo, M, family)
+        if name.startswith("stats_"):
+            tape = {"accept": tape["accept"], "theta_thin10": tape["theta0"][::10],
+                    "acceptance_probability": tape["acceptance_probability"],
+                    "grad_evals": tape["grad_evals"], "theta_last": tape["theta_last"]}
         tape["x_nodes"] = np.array(algo.x)
         tape["w_nodes"] = np.array(algo.w)
         meta = dict(case=name, model=stem, family=family, draws=M, ctor=dict(kw, seed=seed),

@@ -30,10 +30,15 @@ def fit_pair(family, dtype=torch.float64, **kw):
     return k, o
 
 
+DIAG_MODELS = ("normal", "ill-normal")     # targets the tile kernel covers (csrc/klhr_tile.cuh)
+
+
 def replay_both(model_name, data, family, theta, rho, z_init, z_prop, u, init4=None,
                 dtype=torch.float64, xw=None, **fitkw):
     """Run the CUDA replay step and the batched oracle on the same inputs."""
+    force_octet = fitkw.pop("force_octet", False)
     kfit, ofit = fit_pair(family, dtype, **fitkw)
+    kfit.force_octet = force_octet
     if xw is not None:
         kfit.x, kfit.w = np.array(xw[0]), np.array(xw[1])
     model = kb.BSModel(stan_file=f"stan/{model_name}.stan", data=data, device=device())

@@ -18,26 +18,31 @@ GAUSS_TAPES = ["normal_d2_klhr", "normal_d2_klhr_method2", "illnormal_d100_klhr"
 SINH_TAPES = ["funnel_d2_sinh", "funnel_d2_sinh_tight", "ark_t200_sinh", "rosenbrock_d4_sinh"]
 
 
-def _run(name, dtype):
+def _run(name, dtype, force_octet=False):
     t, meta, data = load_tape(name)
     gpu, ref = replay_both(meta["model"], data, meta["family"], t["theta0"], t["rho"], t["z_init"],
                            t["z_prop"], t["u"], init4=t.get("init4"), dtype=dtype,
-                           xw=(t["x_nodes"], t["w_nodes"]))
+                           xw=(t["x_nodes"], t["w_nodes"]), force_octet=force_octet)
     return t, gpu, ref, rel_errors(gpu, ref, meta["family"])
 
 
-@pytest.mark.parametrize("name", GAUSS_TAPES)
-def test_gauss_family_fp64_1e10(name):
-    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float64)
+# the diagonal-Gaussian tapes go through the tile kernel by default; "octet" forces the
+# general kernel so that both device paths are held to the same bar
+KERNELS = [(n, False) for n in GAUSS_TAPES] + [(n, True) for n in GAUSS_TAPES[:4]]
+
+
+@pytest.mark.parametrize("name,force_octet", KERNELS)
+def test_gauss_family_fp64_1e10(name, force_octet):
+    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float64, force_octet)
     tol = 1e-10
     assert em.max() <= tol and es.max() <= tol and ez.max() <= tol and er.max() <= tol
     assert np.array_equal(gpu["accept"], ref["accept"])
     assert np.allclose(gpu["theta"], ref["theta"], rtol=tol, atol=tol)
 
 
-@pytest.mark.parametrize("name", GAUSS_TAPES)
-def test_gauss_family_fp32_1e4(name):
-    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float32)
+@pytest.mark.parametrize("name,force_octet", KERNELS)
+def test_gauss_family_fp32_1e4(name, force_octet):
+    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float32, force_octet)
     tol = 1e-4
     # fp32 round-off occasionally flips a back-tracking decision on the non-Gaussian targets:
     # every draw within 1e-2, 99.5% within the 1e-4 bar, Gaussian targets all within it
@@ -83,9 +88,11 @@ def test_empty_and_ragged_batches():
         th = up(rng.normal(size=(B, 3)))
         rho = rng.normal(size=(B, 3))
         rho /= np.linalg.norm(rho, axis=1, keepdims=True) if B else 1
-        tr = kb.step_replay(model, fit, th, up(rho), up(rng.normal(size=B)), up(rng.normal(size=B)),
-                            up(rng.random(B)))
-        torch.cuda.synchronize()
-        assert tr.eta.shape == (1, B, 2)
-        if B:
-            assert bool(tr.accept.all()) and bool(torch.isfinite(th).all())
+        for force in (False, True):
+            fit.force_octet = force
+            tr = kb.step_replay(model, fit, th, up(rho), up(rng.normal(size=B)), up(rng.normal(size=B)),
+                                up(rng.random(B)))
+            torch.cuda.synchronize()
+            assert tr.eta.shape == (1, B, 2)
+            if B:
+                assert bool(tr.accept.all()) and bool(torch.isfinite(th).all())

@@ -13,9 +13,10 @@ from oracle import batched, stan_models
 pytestmark = pytest.mark.gpu
 
 
-def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, direction=None):
+def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, direction=None, force_octet=False):
     model = kb.BSModel(stan_file=f"stan/{model_name}.stan", data=data, device=device())
     kfit, ofit = fit_pair(family, dtype)
+    kfit.force_octet = force_octet
     D = model.dim()
     rng = np.random.default_rng(seed)
     theta0 = rng.normal(size=(B, D)) * 0.3
@@ -26,14 +27,16 @@ def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, dire
     return model, ofit, theta0, th, tr
 
 
-@pytest.mark.parametrize("model_name,data,family", [
-    ("ill-normal", {"D": 100}, "gauss"), ("funnel", {"D": 4}, "gauss"), ("funnel", {"D": 1}, "sinh"),
-    ("rosenbrock", {"D": 2}, "gauss"), ("ar1", {"N": 20}, "gauss")])
-def test_free_running_step_equals_oracle_on_emitted_variates(model_name, data, family):
+@pytest.mark.parametrize("model_name,data,family,force_octet", [
+    ("ill-normal", {"D": 100}, "gauss", False), ("ill-normal", {"D": 100}, "gauss", True),
+    ("normal", {"D": 300}, "gauss", False), ("normal", {"D": 5}, "gauss", False),
+    ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 1}, "sinh", False),
+    ("rosenbrock", {"D": 2}, "gauss", False), ("ar1", {"N": 20}, "gauss", False)])
+def test_free_running_step_equals_oracle_on_emitted_variates(model_name, data, family, force_octet):
     """The free-running kernel emits the direction and variates it drew; replaying them through
     the oracle must give the same fit, proposal, ratio, flag and state (fp64, 1e-10)."""
-    B, S = 512, 3
-    model, ofit, theta0, th, tr = _trace_run(model_name, data, family, B, S)
+    B, S = 500, 3
+    model, ofit, theta0, th, tr = _trace_run(model_name, data, family, B, S, force_octet=force_octet)
     om = stan_models.make_model(model_name, data)
     theta = theta0.copy()
     for s in range(S):
@@ -84,6 +87,12 @@ def test_philox_streams_are_standard_and_reproducible():
         kb.run(model, kfit, hi, 1, 11, chain_offset=1000, draw_offset=t)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat([lo, hi]), th_a)
+    # the octet kernel draws the same streams as the tile kernel (same chains up to round-off)
+    kfit.force_octet = True
+    oc = up(theta0)
+    kb.run(model, kfit, oc, S, 11)
+    torch.cuda.synchronize()
+    assert torch.allclose(oc, th_a, rtol=1e-9, atol=1e-9)
 
 
 def test_posterior_ill_normal_within_4_mcse():
@@ -107,20 +116,41 @@ def test_posterior_ill_normal_within_4_mcse():
     assert float(summ["rhat"].max()) < 1.05
 
 
-def test_acceptance_rate_matches_reference_tape():
-    """North-star acceptance test: funnel (dims 2), Gaussian family; the reference tape's rate
-    and the device rate agree within 4 binomial standard errors of the tape."""
-    t, meta, data = load_tape("funnel_d2_klhr")
-    n_ref = len(t["accept"]) - 1000
-    p_ref = t["accept"][1000:].mean()                    # post-warm-up draws of the reference chain
-    model = kb.BSModel(stan_file="stan/funnel.stan", data=data, device=device())
-    s = kb.KLHR(model, seed=5, chains=8192, warmup=1000)
-    s.run(1000)
+def _batch_se(x, nb=30):
+    """Standard error of the mean of an autocorrelated series by batch means."""
+    x = np.asarray(x, dtype=np.float64)
+    n = (len(x) // nb) * nb
+    bm = x[:n].reshape(nb, -1, *x.shape[1:]).mean(1)
+    return bm.std(0, ddof=1) / np.sqrt(nb)
+
+
+@pytest.mark.parametrize("tape,cls,burn", [
+    ("stats_funnel_d2_klhr_noadapt", "KLHR", 3000), ("stats_rosenbrock_d4_klhr_noadapt", "KLHR", 3000),
+    ("stats_funnel_d2_sinh_noadapt", "KLHRSINH", 1000)])
+def test_acceptance_and_posterior_match_reference_tape(tape, cls, burn):
+    """North-star tests 2 and 3 against long runs of the UNMODIFIED reference (tests/golden
+    stats_* tapes, adaptation off on both sides so the direction law is identical):
+    acceptance rate within 4 binomial/batch standard errors, posterior means and variances
+    within 4 MCSE."""
+    t, meta, data = load_tape(tape)
+    acc_ref = t["accept"][burn:].astype(float)
+    p_ref, se_ref = acc_ref.mean(), max(_batch_se(acc_ref), np.sqrt(acc_ref.mean() * (1 - acc_ref.mean()) / len(acc_ref)))
+    model = kb.BSModel(stan_file=f"stan/{meta['model']}.stan", data=data, device=device())
+    s = getattr(kb, cls)(model, seed=5, chains=8192, warmup=0)
+    s.run(1500)                                          # burn-in from the N(0, 0.1^2) start
     a0 = s._accept_count.clone()
-    s.run(500)
-    p_dev = float((s._accept_count - a0).double().mean()) / 500
-    se = np.sqrt(p_ref * (1 - p_ref) / n_ref)
-    assert abs(p_dev - p_ref) <= 4 * se, (p_dev, p_ref, se)
+    S = 1000
+    s1, s2 = s.run(S, chain_stats=True)
+    p_dev = float((s._accept_count - a0).double().mean()) / S
+    assert abs(p_dev - p_ref) <= 4 * se_ref, (p_dev, p_ref, se_ref)
+    summ = chain_summary(s1, s2, S)
+    th = t["theta_thin10"][burn // 10:]
+    m_ref, v_ref = th.mean(0), th.var(0, ddof=1)
+    se_m = _batch_se(th)
+    se_v = _batch_se((th - m_ref) ** 2)
+    dm = np.abs(summ["mean"].cpu().numpy() - m_ref) / np.sqrt(se_m ** 2 + summ["mcse_mean"].cpu().numpy() ** 2)
+    dv = np.abs(summ["var"].cpu().numpy() - v_ref) / np.sqrt(se_v ** 2 + summ["mcse_var"].cpu().numpy() ** 2)
+    assert dm.max() <= 4 and dv.max() <= 4, (dm, dv)
 
 
 def test_funnel_sinh_posterior_marginal():
