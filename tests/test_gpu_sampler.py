@@ -143,6 +143,8 @@ def test_acceptance_and_posterior_match_reference_tape(tape, cls, burn):
     s1, s2 = s.run(S, chain_stats=True)
     p_dev = float((s._accept_count - a0).double().mean()) / S
     assert abs(p_dev - p_ref) <= 4 * se_ref, (p_dev, p_ref, se_ref)
+    if "rosenbrock" in tape:
+        return        # one reference chain of 20k draws has not mixed on the banana (posterior checked below)
     summ = chain_summary(s1, s2, S)
     th = t["theta_thin10"][burn // 10:]
     m_ref, v_ref = th.mean(0), th.var(0, ddof=1)
@@ -151,6 +153,21 @@ def test_acceptance_and_posterior_match_reference_tape(tape, cls, burn):
     dm = np.abs(summ["mean"].cpu().numpy() - m_ref) / np.sqrt(se_m ** 2 + summ["mcse_mean"].cpu().numpy() ** 2)
     dv = np.abs(summ["var"].cpu().numpy() - v_ref) / np.sqrt(se_v ** 2 + summ["mcse_var"].cpu().numpy() ** 2)
     assert dm.max() <= 4 and dv.max() <= 4, (dm, dv)
+
+
+def test_rosenbrock_posterior_against_analytic_truth():
+    """stan/rosenbrock.stan: v ~ N(1,1), theta | v ~ N(v^2, 0.1): E v = 1, Var v = 1, E theta = 2,
+    Var theta = 6.01 (SURVEY.md 8c iii).  Long run, many chains, 4 MCSE."""
+    model = kb.BSModel(stan_file="stan/rosenbrock.stan", data={"D": 2}, device=device())
+    s = kb.KLHR(model, seed=8, chains=4096, warmup=0)
+    s.run(30_000)
+    S = 20_000
+    s1, s2 = s.run(S, chain_stats=True)
+    summ = chain_summary(s1, s2, S)
+    mean, var = summ["mean"].cpu().numpy(), summ["var"].cpu().numpy()
+    zm = np.abs(mean - [1, 1, 2, 2]) / summ["mcse_mean"].cpu().numpy()
+    zv = np.abs(var - [1, 1, 6.01, 6.01]) / summ["mcse_var"].cpu().numpy()
+    assert zm.max() <= 4 and zv.max() <= 4, (mean, var, zm, zv)
 
 
 def test_funnel_sinh_posterior_marginal():
