@@ -103,17 +103,18 @@ struct Philox {
         }
         out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
     }
-    // Four blocks whose counters differ only in c3 = slot0 + stride * b, advanced round by round
+    // NB blocks whose counters differ only in c3 = slot0 + stride * b, advanced round by round
     // so that the 8 independent multiplies per round overlap (one block alone is a serial chain).
-    __device__ static __forceinline__ void block4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t slot0,
-                                                   uint32_t stride, uint32_t k0, uint32_t k1, uint32_t out[4][4]) {
-        uint32_t s[4][4];
+    template <int NB>
+    __device__ static __forceinline__ void blockN(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t slot0,
+                                                   uint32_t stride, uint32_t k0, uint32_t k1, uint32_t out[NB][4]) {
+        uint32_t s[NB][4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { s[b][0] = c0; s[b][1] = c1; s[b][2] = c2; s[b][3] = slot0 + stride * b; }
+        for (int b = 0; b < NB; ++b) { s[b][0] = c0; s[b][1] = c1; s[b][2] = c2; s[b][3] = slot0 + stride * b; }
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < NB; ++b) {
                 const uint64_t p0 = (uint64_t)M0 * s[b][0];
                 const uint64_t p1 = (uint64_t)M1 * s[b][2];
                 const uint32_t n0 = (uint32_t)(p1 >> 32) ^ s[b][1] ^ k0;
@@ -123,7 +124,7 @@ struct Philox {
             k0 += W0; k1 += W1;
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int q = 0; q < 4; ++q) out[b][q] = s[b][q];
     }

@@ -55,9 +55,11 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
     const int L = threadIdx.x;
     const int o = L >> 3, j = L & 7;
     const unsigned om = oct_mask();
-    XT* xs = reinterpret_cast<XT*>(smem_raw);            // [32][Dx]
-    float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);   // [D]
-    float* s_mean = s_sd + D;                            // [n_cols][D]
+    // shared memory: w[D] (R) | xs[32][Dx] (XT) | sd[D] (float) | mean[max(n_cols,1)][D] (float)
+    R* s_w = reinterpret_cast<R*>(smem_raw);
+    XT* xs = reinterpret_cast<XT*>(s_w + ((D + 1) & ~1));
+    float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);
+    float* s_mean = s_sd + D;
     const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
 
     const long long tile0 = (long long)blockIdx.x * kTileChains;
@@ -66,13 +68,14 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
     R* g_theta = reinterpret_cast<R*>(a.theta);
     const R* g_w = reinterpret_cast<const R*>(a.mp.p0);
 
+    for (int i = L; i < D; i += kTileChains) s_w[i] = kScaled ? g_w[i] : R(1);
     if constexpr (!kReplay) {
         const R* g_sd = reinterpret_cast<const R*>(a.dir.sd);
         const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
         for (int i = L; i < D; i += kTileChains) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
-        for (int i = L; i < n_cols * D; i += kTileChains) s_mean[i] = (float)g_mean[i];
-        __syncwarp();
+        for (int i = L; i < (n_cols ? n_cols : 1) * D; i += kTileChains) s_mean[i] = n_cols ? (float)g_mean[i] : 0.0f;
     }
+    __syncwarp();
 
     const R tol = (R)a.fp.tol;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
@@ -104,71 +107,88 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
         }
         R my_ss = 1, my_A = 0, my_B = 0;
         // -------------------------------------------------------------------- D-phase
+        R cp_next = oct_bcast(c_pend, 0, om);
+        int col_next = oct_bcast(jcol, 0, om);
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
             const int cs = 4 * p + o;
             const long long c = tile0 + cs;
-            const R cp = oct_bcast(c_pend, p, om);
-            const int col = oct_bcast(jcol, p, om);
+            const R cp = cp_next;                          // pending move of this pass's chain
+            const int col = col_next;
+            cp_next = oct_bcast(c_pend, (p + 1) & 7, om);  // fetched one pass ahead: hides the shuffle latency
+            col_next = oct_bcast(jcol, (p + 1) & 7, om);
             if (c >= a.B) continue;                       // octet-uniform
             if (last && cp == R(0)) continue;
             R* row = g_theta + c * D;
             XT* xr = xs + (size_t)cs * Dx;
-            const float* mcol = n_cols ? s_mean + (size_t)col * D : nullptr;
+            const float* mcol = s_mean + (size_t)col * D;
             const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
             const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
+            const bool pend = cp != R(0);
             R ss = 0, sA = 0, sB = 0;
+            // element i = g0 + j + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128), word r.
+            // Each half handles blocks t = 2h, 2h+1 (8 elements per lane).
             for (int g0 = 0; g0 < D; g0 += 128) {
-                // element i = g0 + j + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128), word r
-                // 1. issue the loads of this chain's theta slice (and of the previous x when a move is
-                //    pending); nothing below depends on them until step 3, so the L2 latency hides
-                //    behind the Philox / Box-Muller arithmetic of step 2
-                R th[16];
-                XT xo[16];
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    const int i = g0 + j + 8 * (s >> 2) + 32 * (s & 3);
-                    th[s] = i < D ? row[i] : R(0);
-                    xo[s] = (cp != R(0) && i < D) ? xr[i] : XT(0);
-                }
-                // 2. 16 normals: four Philox blocks advanced in lockstep, eight Box-Muller pairs
-                float z[16];
-                if constexpr (!kReplay) {
-                    if (!last) {
-                        uint32_t w[4][4];
-                        Philox::block4(c0, c1, d0, kSlotDir + (uint32_t)j + (uint32_t)(g0 / 4), 8u, k0, k1d, w);
+                for (int h = 0; h < 2; ++h) {
+                    if (g0 + 16 * h >= D) break;          // octet-uniform: no live element in this half
+                    // 1. issue every load of the half first (theta slice from L2, previous x, weights,
+                    //    direction scales); their latency hides behind the RNG arithmetic of step 2
+                    R th[8], wv[8];
+                    XT xo[8];
+                    float sdv[8], mv[8];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
-                            box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
+                    for (int s = 0; s < 8; ++s) {
+                        const int i = g0 + j + 8 * (2 * h + (s >> 2)) + 32 * (s & 3);
+                        const bool live = i < D;
+                        th[s] = live ? row[i] : R(0);
+                        xo[s] = (pend && live) ? xr[i] : XT(0);
+                        wv[s] = live ? s_w[i] : R(0);
+                        if constexpr (!kReplay) {
+                            sdv[s] = live ? s_sd[i] : 0.0f;
+                            mv[s] = live ? mcol[i] : 0.0f;
                         }
                     }
-                }
-                // 3. apply the pending move, form the new x and the three sums
-#pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    const int i = g0 + j + 8 * (s >> 2) + 32 * (s & 3);
-                    if (i < D) {
-                        R t0 = th[s];
-                        if (cp != R(0)) {
-                            t0 = t0 + cp * (R)xo[s];
-                            row[i] = t0;
-                        }
+                    // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
+                    float z[8];
+                    if constexpr (!kReplay) {
                         if (!last) {
-                            R x;
-                            if constexpr (kReplay) {
-                                x = reinterpret_cast<const R*>(a.rho)[c * D + i];
-                                xr[i] = (XT)x;
-                            } else {
-                                const float xf = fmaf(s_sd[i], z[s], mcol ? mcol[i] : 0.0f);
-                                xr[i] = (XT)xf;
-                                x = (R)xf;
+                            uint32_t w[2][4];
+                            Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
+                                              k0, k1d, w);
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
+                                box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
                             }
-                            const R xt = x + tol;
-                            ss += xt * xt;
-                            const R xw = x * Model::wgt(i, a.mp);
-                            sA += x * xw;
-                            sB += t0 * xw;
+                        }
+                    }
+                    // 3. apply the pending move, form the new x and the three sums
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int i = g0 + j + 8 * (2 * h + (s >> 2)) + 32 * (s & 3);
+                        if (i < D) {
+                            R t0 = th[s];
+                            if (pend) {
+                                t0 = t0 + cp * (R)xo[s];
+                                row[i] = t0;
+                            }
+                            if (!last) {
+                                R x;
+                                if constexpr (kReplay) {
+                                    x = reinterpret_cast<const R*>(a.rho)[c * D + i];
+                                    xr[i] = (XT)x;
+                                } else {
+                                    const float xf = fmaf(sdv[s], z[s], mv[s]);
+                                    xr[i] = (XT)xf;
+                                    x = (R)xf;
+                                }
+                                const R xt = x + tol;
+                                ss += xt * xt;
+                                const R xw = x * wv[s];
+                                sA += x * xw;
+                                sB += t0 * xw;
+                            }
                         }
                     }
                 }
@@ -244,7 +264,8 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
     const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int xbytes = replay ? (int)sizeof(R) : 4;
     a.Dpad = pad_dim(a.mp.D, xbytes);
-    const size_t smem = (size_t)kTileChains * a.Dpad * xbytes + (size_t)(1 + n_cols) * a.mp.D * sizeof(float);
+    const size_t smem = (size_t)((a.mp.D + 1) & ~1) * sizeof(R) + (size_t)kTileChains * a.Dpad * xbytes +
+                        (size_t)(1 + (n_cols ? n_cols : 1)) * a.mp.D * sizeof(float);
     if (smem > 227 * 1024) return -20;
     const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
                             : (const void*)tile_kernel<R, kScaled, float, false>;
