@@ -347,7 +347,8 @@ def run_b200(args):
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "klhr::step_kernel<double, DiagNormal<double,true>, 2, false, false>",
+                         "kernel": ("klhr::tile_kernel (csrc/klhr_tile.cuh)" if info["threads"] == 32 else
+                                    "klhr::step_kernel (csrc/klhr_step.cuh)"),
                          "algorithmic_bytes_per_chain_draw": bytes_per_draw,
                          "note": f"{S} draws fused per launch: actual HBM traffic is (2*D*{rb}+16)/{S} B per "
                                  "chain-draw; achieved counts SURVEY 8(d) algorithmic bytes"},
