@@ -79,11 +79,13 @@ typedef struct klhr_fit {
  * probabilities cdf[0..n_cols-1] (eigen_method_one) or n_cols == 1 (method two: the host
  * pre-combines the eigenvectors).  A NULL `mean_cols` means a zero mean. */
 typedef struct klhr_direction {
-    const void* mean_cols;       /* [n_cols][D] reals or NULL                              */
+    const void* mean_cols;       /* [n_cols - n_zero_cols][D] reals or NULL                */
     const void* sd;              /* [D] reals, sqrt(_cov); NULL = ones                     */
     const void* cdf;             /* [n_cols] reals, last entry 1; NULL when n_cols <= 1    */
-    int32_t n_cols;
-    int32_t reserved;
+    int32_t n_cols;              /* number of candidate mean columns                       */
+    int32_t n_zero_cols;         /* trailing columns that are identically zero and NOT stored
+                                    in mean_cols: the "isotropic" extra column of
+                                    eigen_method_one (klhr.py:64-66) -> 1, else 0           */
 } klhr_direction_t;
 
 /* Per-draw trace buffers, all optional (NULL = not written).  Layout [step][chain][..]. */

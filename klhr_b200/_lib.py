@@ -37,7 +37,7 @@ class FitDesc(C.Structure):
 
 class DirectionDesc(C.Structure):
     _fields_ = [("mean_cols", C.c_void_p), ("sd", C.c_void_p), ("cdf", C.c_void_p),
-                ("n_cols", C.c_int32), ("reserved", C.c_int32)]
+                ("n_cols", C.c_int32), ("n_zero_cols", C.c_int32)]
 
 
 class TraceDesc(C.Structure):

@@ -217,6 +217,8 @@ static int fill_run(StepArgs& a, const klhr_model_t* model, const klhr_fit_t* fi
     if (dir) {
         a.dir = *dir;
         if (a.dir.mean_cols && a.dir.n_cols < 1) return fail(-11, "direction: n_cols must be >= 1 with mean_cols");
+        if (a.dir.n_zero_cols < 0 || a.dir.n_zero_cols > 1 || (a.dir.mean_cols && a.dir.n_zero_cols >= a.dir.n_cols))
+            return fail(-11, "direction: n_zero_cols must be 0 or 1 and smaller than n_cols");
         if (a.dir.mean_cols && a.dir.n_cols > 1 && !a.dir.cdf) return fail(-11, "direction: cdf needed when n_cols > 1");
         if (!a.dir.mean_cols) a.dir.n_cols = 0;
     }

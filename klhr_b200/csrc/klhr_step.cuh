@@ -28,6 +28,7 @@ struct StepArgs {
     void* theta;
     long long B;
     int Dpad;
+    int tile_mean_smem;      // tile kernel: direction-mean columns staged in shared memory
     // replay inputs
     const void* rho;
     const void* z_init;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
         const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
         for (int i = threadIdx.x; i < D; i += blockDim.x) s_sd[i] = g_sd ? g_sd[i] : R(1);
         if (g_mean)
-            for (int i = threadIdx.x; i < a.dir.n_cols * D; i += blockDim.x) s_mean[i] = g_mean[i];
+            for (int i = threadIdx.x; i < (a.dir.n_cols - a.dir.n_zero_cols) * D; i += blockDim.x) s_mean[i] = g_mean[i];
     }
     if constexpr (kAccum) {
         const R* g_shift = reinterpret_cast<const R*>(a.acc.shift);
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
                         const R* cdf = reinterpret_cast<const R*>(a.dir.cdf);
                         while (j < a.dir.n_cols - 1 && u_col >= cdf[j]) ++j;
                     }
-                    mcol = s_mean + (size_t)j * D;
+                    mcol = j < a.dir.n_cols - a.dir.n_zero_cols ? s_mean + (size_t)j * D : nullptr;   // zero column
                 }
                 R ss = 0;
                 // element i = g0 + lane + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128),

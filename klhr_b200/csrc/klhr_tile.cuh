@@ -55,12 +55,19 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
     const int L = threadIdx.x;
     const int o = L >> 3, j = L & 7;
     const unsigned om = oct_mask();
-    // shared memory: w[D] (R) | xs[32][Dx] (XT) | sd[D] (float) | mean[max(n_cols,1)][D] (float)
+    // shared memory: w[D] (R) | xs[32][Dx] (XT) | sd[D] (float) | cdf[n_cols] (float) | mean[n_sm][D] (float).
+    // Every byte counts: 14 one-warp CTAs must fit per SM for the 2048 tiles of B = 65 536 to be
+    // resident in one wave, so the stored direction-mean columns go to shared memory only when
+    // they fit that budget (n_sm = a.tile_mean_smem columns), otherwise they are read from global.
     R* s_w = reinterpret_cast<R*>(smem_raw);
     XT* xs = reinterpret_cast<XT*>(s_w + ((D + 1) & ~1));
     float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);
-    float* s_mean = s_sd + D;
     const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+    const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
+    float* s_cdf = s_sd + D;
+    float* s_mean = s_cdf + n_cols;
+    const bool mean_in_smem = a.tile_mean_smem != 0;
+    const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
 
     const long long tile0 = (long long)blockIdx.x * kTileChains;
     const long long c_own = tile0 + 4 * j + o;           // the chain this thread owns in the fit phase
@@ -71,9 +78,11 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
     for (int i = L; i < D; i += kTileChains) s_w[i] = kScaled ? g_w[i] : R(1);
     if constexpr (!kReplay) {
         const R* g_sd = reinterpret_cast<const R*>(a.dir.sd);
-        const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
         for (int i = L; i < D; i += kTileChains) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
-        for (int i = L; i < (n_cols ? n_cols : 1) * D; i += kTileChains) s_mean[i] = n_cols ? (float)g_mean[i] : 0.0f;
+        if (n_cols > 1)
+            for (int i = L; i < n_cols; i += kTileChains) s_cdf[i] = (float)reinterpret_cast<const R*>(a.dir.cdf)[i];
+        if (mean_in_smem)
+            for (int i = L; i < n_stored * D; i += kTileChains) s_mean[i] = (float)g_mean[i];
     }
     __syncwarp();
 
@@ -99,10 +108,8 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
             } else {
                 const unsigned long long cid = (unsigned long long)(a.chain_offset + c_own);
                 chain_scalars<R>((uint32_t)cid, (uint32_t)(cid >> 32), d0, k0, k1d, u_col, z_init, z_prop, u);
-                if (n_cols > 1) {
-                    const R* cdf = reinterpret_cast<const R*>(a.dir.cdf);
-                    while (jcol < n_cols - 1 && u_col >= cdf[jcol]) ++jcol;     // searchsorted 'right', klhr.py:147
-                }
+                if (n_cols > 1)                           // searchsorted(cdf, u, 'right'), klhr.py:147
+                    while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
             }
         }
         R my_ss = 1, my_A = 0, my_B = 0;
@@ -121,7 +128,9 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
             if (last && cp == R(0)) continue;
             R* row = g_theta + c * D;
             XT* xr = xs + (size_t)cs * Dx;
-            const float* mcol = s_mean + (size_t)col * D;
+            const bool has_mean = col < n_stored;         // a zero column (klhr.py:64-66) is not stored
+            const R* mcol_g = g_mean + (size_t)(has_mean ? col : 0) * D;
+            const float* mcol_s = s_mean + (size_t)(has_mean ? col : 0) * D;
             const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
             const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
             const bool pend = cp != R(0);
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
                         wv[s] = live ? s_w[i] : R(0);
                         if constexpr (!kReplay) {
                             sdv[s] = live ? s_sd[i] : 0.0f;
-                            mv[s] = live ? mcol[i] : 0.0f;
+                            mv[s] = (live && has_mean) ? (mean_in_smem ? mcol_s[i] : (float)__ldg(mcol_g + i)) : 0.0f;
                         }
                     }
                     // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
@@ -261,11 +270,17 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
 template <typename R, bool kScaled>
 int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, LaunchInfo* info) {
     StepArgs a = args_in;
-    const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int xbytes = replay ? (int)sizeof(R) : 4;
     a.Dpad = pad_dim(a.mp.D, xbytes);
-    const size_t smem = (size_t)((a.mp.D + 1) & ~1) * sizeof(R) + (size_t)kTileChains * a.Dpad * xbytes +
-                        (size_t)(1 + (n_cols ? n_cols : 1)) * a.mp.D * sizeof(float);
+    const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+    const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
+    size_t smem = (size_t)((a.mp.D + 1) & ~1) * sizeof(R) + (size_t)kTileChains * a.Dpad * xbytes +
+                  (size_t)(a.mp.D + n_cols) * sizeof(float);
+    // budget for 14 CTAs per SM: (228 KB / 14) minus the 1 KB the driver reserves per CTA
+    const size_t budget = 228 * 1024 / 14 - 1024;
+    const size_t mean_bytes = (size_t)n_stored * a.mp.D * sizeof(float);
+    a.tile_mean_smem = (n_stored > 0 && smem + mean_bytes <= budget) ? 1 : 0;
+    if (a.tile_mean_smem) smem += mean_bytes;
     if (smem > 227 * 1024) return -20;
     const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
                             : (const void*)tile_kernel<R, kScaled, float, false>;

@@ -142,11 +142,12 @@ class Direction:
     mean_cols: torch.Tensor = None     # (n_cols, D) or None (zero mean)
     sd: torch.Tensor = None            # (D,) sqrt(_cov) or None (ones)
     cdf: torch.Tensor = None           # (n_cols,) cumulative column probabilities
+    n_zero_cols: int = 0               # trailing all-zero columns not stored in mean_cols (klhr.py:64-66)
 
     def descriptor(self):
-        n = 0 if self.mean_cols is None else int(self.mean_cols.shape[0])
+        n = 0 if self.mean_cols is None else int(self.mean_cols.shape[0]) + int(self.n_zero_cols)
         return _lib.DirectionDesc(mean_cols=_ptr(self.mean_cols), sd=_ptr(self.sd), cdf=_ptr(self.cdf),
-                                  n_cols=n)
+                                  n_cols=n, n_zero_cols=int(self.n_zero_cols))
 
 
 def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Direction = None,

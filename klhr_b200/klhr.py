@@ -110,11 +110,14 @@ class KLHR(MCMCBase):
         p = lam / np.sum(lam)
         sd = torch.as_tensor(np.sqrt(np.maximum(self._cov, 0.0)), dtype=dt, device=dev).contiguous()
         if self._eigen_method_one:
-            cols = torch.as_tensor(np.ascontiguousarray(self._eigvecs.T), dtype=dt, device=dev).contiguous()
+            # the extra column J is identically zero (klhr.py:64-66): it is not shipped to the device
+            cols = torch.as_tensor(np.ascontiguousarray(self._eigvecs[:, :self.J].T), dtype=dt, device=dev)
+            cols = cols.reshape(self.J, self.D).contiguous()
             cdf = np.cumsum(p)
             cdf /= cdf[-1]
             cdf_t = torch.as_tensor(cdf, dtype=dt, device=dev).contiguous()
-            self._direction = engine.Direction(mean_cols=cols, sd=sd, cdf=cdf_t)
+            self._direction = engine.Direction(mean_cols=cols if self.J > 0 else None, sd=sd, cdf=cdf_t,
+                                               n_zero_cols=1 if self.J > 0 else 0)
         else:
             wgt = p if self._eigen_weights_normalised else lam
             m = np.sum(wgt * self._eigvecs, axis=1) if self._eigvecs.shape[1] else np.zeros(self.D)

@@ -95,6 +95,35 @@ def test_philox_streams_are_standard_and_reproducible():
     assert torch.allclose(oc, th_a, rtol=1e-9, atol=1e-9)
 
 
+def test_direction_law_columns_and_kernel_agreement():
+    """klhr.py:143-153 with eigen_method_one: column j ~ Cat(p), x ~ N(v_j, diag(cov)); the extra
+    zero column is not stored on the device.  Tile and octet kernels must draw the same rho."""
+    D, B = 40, 20000
+    model = kb.BSModel(stan_file="stan/normal.stan", data={"D": D}, device=device())
+    kfit, _ = fit_pair("gauss")
+    e = np.zeros((2, D))
+    e[0, 3] = 1.0
+    e[1, 17] = -1.0
+    p = np.array([0.5, 0.3, 0.2])
+    direction = kb.Direction(mean_cols=up(e), sd=up(np.full(D, 1e-3)), cdf=up(np.cumsum(p)), n_zero_cols=1)
+    rhos = []
+    for force in (False, True):
+        kfit.force_octet = force
+        th = up(np.zeros((B, D)))
+        tr = kb.Trace(1, B, D, 2, torch.float64, device(), variates=True, rho=True)
+        kb.run(model, kfit, th, 1, 99, direction, trace=tr)
+        torch.cuda.synchronize()
+        rhos.append(tr.rho[0].cpu().numpy())
+    assert np.allclose(rhos[0], rhos[1], rtol=1e-9, atol=1e-12)
+    rho = rhos[0]
+    assert np.allclose(np.linalg.norm(rho + 1e-12, axis=1), 1, atol=1e-10)
+    f0 = (rho[:, 3] > 0.99).mean()
+    f1 = (rho[:, 17] < -0.99).mean()
+    iso = (np.abs(rho).max(1) < 0.9).mean()               # zero-mean column: isotropic direction
+    for f, q in ((f0, 0.5), (f1, 0.3), (iso, 0.2)):
+        assert abs(f - q) < 5 * np.sqrt(q * (1 - q) / B)
+
+
 def test_posterior_ill_normal_within_4_mcse():
     """North-star posterior test: means and variances within 4 MCSE of the truth
     (stan/ill-normal.stan:5: var_i = i^2 / D)."""

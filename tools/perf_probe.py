@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--tag", default="")
 ap.add_argument("--octet", action="store_true")
+ap.add_argument("--direction", action="store_true", help="eigen_method_one law: 2 mean columns + zero column")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 dt = torch.float64 if a.dtype == "f64" else torch.float32
@@ -26,14 +27,19 @@ D = model.dim()
 th = (torch.randn(a.chains, D, dtype=torch.float64, device=dev) * 0.5).to(dt).contiguous()
 acc = torch.zeros(a.chains, dtype=torch.int64, device=dev)
 ev = torch.zeros(1, dtype=torch.int64, device=dev)
-kb.run(model, fit, th, 50, 1, accept_count=acc, evals_total=ev)
+direction = None
+if a.direction:
+    cols = torch.randn(2, D, dtype=torch.float64, device=dev).to(dt).contiguous()
+    direction = kb.Direction(mean_cols=cols, sd=torch.ones(D, dtype=dt, device=dev),
+                             cdf=torch.tensor([0.4, 0.7, 1.0], dtype=dt, device=dev), n_zero_cols=1)
+kb.run(model, fit, th, 50, 1, direction, accept_count=acc, evals_total=ev)
 torch.cuda.synchronize()
 acc.zero_(); ev.zero_()
 times = []
 for r in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kb.run(model, fit, th, a.draws, 1, draw_offset=50 + r * a.draws, accept_count=acc, evals_total=ev)
+    kb.run(model, fit, th, a.draws, 1, direction, draw_offset=50 + r * a.draws, accept_count=acc, evals_total=ev)
     e1.record()
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
