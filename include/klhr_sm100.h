@@ -53,8 +53,9 @@ typedef struct klhr_model {
 } klhr_model_t;
 
 #define KLHR_MAX_NODES 32
-/* klhr_fit_t.flags: run the general octet-per-chain kernel even where the faster tile kernel
- * (diagonal-Gaussian targets, Gaussian family) applies -- used by the parity tests to cover both */
+/* klhr_fit_t.flags: run the general octet-per-chain kernel even where the faster thread-per-chain
+ * kernels (tile kernel: diagonal-Gaussian targets with the Gaussian family; chain kernel: every
+ * other case whose rho tile fits in shared memory) apply -- the parity tests cover both paths */
 #define KLHR_FIT_FORCE_OCTET 1
 
 /* Line-fit configuration: the reference's constructor arguments that reach the fit

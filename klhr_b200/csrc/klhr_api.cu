@@ -6,7 +6,7 @@
 #include <cmath>
 #include <string>
 
-#include "klhr_tile.cuh"
+#include "klhr_chain.cuh"
 
 namespace klhr {
 
@@ -81,9 +81,31 @@ static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
            (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && a.fp.N <= kMaxNodes;
 }
 
+// The chain kernel (thread-per-chain fit, model-generic line setup) covers every target and both
+// families as long as its rho tile fits a modest shared-memory budget; like the tile kernel it
+// has no in-kernel accumulators and no thinned-draw output.
+static bool chain_applies(const StepArgs& a, int dtype, bool replay, bool accum, int flags) {
+    return !(flags & KLHR_FIT_FORCE_OCTET) && !accum && !a.acc.draws &&
+           chain_smem_bytes(a, dtype == KLHR_F64 ? 8 : 4, replay) <= 20 * 1024;   // larger D: the octet kernel keeps theta resident
+}
+
+static int dispatch_chain(const StepArgs& a, int dtype, int family, bool replay, cudaStream_t st, LaunchInfo* info) {
+    switch (a.mp.id) {
+        case KLHR_MODEL_NORMAL: return launch_chain_normal(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_ILL_NORMAL: return launch_chain_ill_normal(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_FUNNEL: return launch_chain_funnel(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_CORR_NORMAL: return launch_chain_corr_normal(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_AR1: return launch_chain_ar1(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_ARK: return launch_chain_ark(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_ROSENBROCK: return launch_chain_rosenbrock(a, dtype, family, replay, st, info);
+    }
+    return fail(-2, "unknown model id");
+}
+
 static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, bool accum, cudaStream_t st,
                          LaunchInfo* info, int flags) {
     if (tile_applies(a, family, accum, flags)) return launch_tile(a, dtype, replay, st, info);
+    if (chain_applies(a, dtype, replay, accum, flags)) return dispatch_chain(a, dtype, family, replay, st, info);
     switch (a.mp.id) {
         case KLHR_MODEL_NORMAL: return launch_step_normal(a, dtype, family, replay, accum, st, info);
         case KLHR_MODEL_ILL_NORMAL: return launch_step_ill_normal(a, dtype, family, replay, accum, st, info);

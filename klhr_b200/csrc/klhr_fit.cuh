@@ -47,12 +47,14 @@ __device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitP
     Jet<R> J = Model::eval(cf, xi);
     nev = 1;
     const R gt1sq = (R)fp.gtol1 * (R)fp.gtol1;
+    const unsigned wm = __activemask();
     for (int it = 0; it < fp.n1; ++it) {
         const bool concave = J.l2 < R(0);
         // |l'| / sqrt(-l'') <= gtol1, written without the square root and the division
         const bool conv = concave && (J.l1 * J.l1 <= gt1sq * (-J.l2));
         done = done || conv || !r_finite(J.l);
-        if (done) break;
+        if (!__any_sync(wm, !done)) break;      // lock-step: finished chains idle, nobody serialises
+        if (done) continue;
         const R newton = concave ? -J.l1 / J.l2 : R(0);
         const R step = concave ? r_clamp(newton, -R(8) * trust, R(8) * trust) : r_clamp(J.l1, -trust, trust);
         nev += kOct;
@@ -110,7 +112,8 @@ struct KLState {
 // Solve (H) p = -g by Cholesky, entry by entry like oracle/batched.py:_chol_solve.
 template <typename R, int n>
 __device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R (&g)[n], R (&p)[n]) {
-    R L[n][n];
+    // one division per pivot (its reciprocal), multiplications everywhere else
+    R L[n][n], iL[n];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < n; ++j) {
@@ -120,12 +123,13 @@ __device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R 
         ok = ok && (acc > R(0));
         const R ljj = r_sqrt(acc > R(0) ? acc : R(1));
         L[j][j] = ljj;
+        iL[j] = R(1) / ljj;
 #pragma unroll
         for (int i = j + 1; i < n; ++i) {
             R a2 = H[i][j];
 #pragma unroll
             for (int k = 0; k < j; ++k) a2 = a2 - L[i][k] * L[j][k];
-            L[i][j] = a2 / ljj;
+            L[i][j] = a2 * iL[j];
         }
     }
     R y[n];
@@ -134,14 +138,14 @@ __device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R 
         R acc = -g[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) acc = acc - L[i][k] * y[k];
-        y[i] = acc / L[i][i];
+        y[i] = acc * iL[i];
     }
 #pragma unroll
     for (int i = n - 1; i >= 0; --i) {
         R acc = y[i];
 #pragma unroll
         for (int k = i + 1; k < n; ++k) acc = acc - L[k][i] * p[k];
-        p[i] = acc / L[i][i];
+        p[i] = acc * iL[i];
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) ok = ok && r_finite(p[i]);
@@ -247,7 +251,11 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         const R w = (R)fp.w[n];
         const R a = ((R)fp.cx[n] + q.e) * invd;
         const R ac = r_clamp(a, -c, c);
-        const R sh = r_sinh(ac), ch = r_cosh(ac), th = r_tanh(ac);
+        // sinh, cosh, tanh and log cosh from ONE exponential (|ac| <= scale_clip = 300 keeps e^ac
+        // finite in fp64); absolute accuracy ~1 ulp of cosh, which is what T and the KL sums need
+        const R E = r_exp(ac), Ei = R(1) / E;
+        const R sh = R(0.5) * (E - Ei), ch = R(0.5) * (E + Ei);
+        const R th = sh / ch;
         const R sech2 = R(1) - th * th;
         const R T = q.m + q.s * sh;
         const Jet<R> J = Model::eval(cf, T);
@@ -307,63 +315,79 @@ __device__ __forceinline__ R scale_of(const R (&eta)[n], const FitParams& fp) {
 }
 
 // ------------------------------------------------------------------ stage 2: damped Newton on KL
+// Written as a lock-step state machine: every trip of the ONE loop performs exactly one KL
+// evaluation (the expensive, uniform part) for every chain of the warp, followed by a short
+// per-chain decision (accept / halve / new Newton direction).  The per-chain sequence of
+// evaluations is exactly the nested loop of oracle/batched.py:stage2_newton, but chains that
+// sit in different phases (back-tracking vs. new direction) no longer serialise each other:
+// with 4 octets (or 32 single-thread chains) per warp the nested form ran one group at a time.
 template <int G, typename R, typename Model, int n>
 __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
                               unsigned m, int& nev, bool& converged) {
+    const unsigned wm = __activemask();        // the lanes that entered together stay in lock-step
     KLState<R, n> S;
-    kl_eval<G, R, Model, n>(cf, eta, fp, lane, m, S);
-    nev = 1;
-    bool conv = false;
-    for (int it = 0; it < fp.n2; ++it) {
-        R gmax = 0;
-        bool gnan = false;
+    R p[n], trial[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-            gmax = r_max(gmax, r_abs(S.g[i]));
-            gnan = gnan || (S.g[i] != S.g[i]);
-        }
-        if (!gnan && gmax <= (R)fp.gtol2) { conv = true; break; }
-        R p[n];
-        newton_direction<R, n>(S, fp, p);
-        R gp = 0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) gp += S.g[i] * p[i];
-        if (!r_finite(gp)) gp = 0;
-        const R s_cur = scale_of<R, n>(eta, fp);
-        const bool in_basin = !gnan && gmax <= (R)fp.basin;
-        R t = 1;
-        bool accepted = false;
-        for (int bt = 0; bt < fp.nb; ++bt) {
-            R trial[n];
-            trial[0] = eta[0] + t * p[0] * s_cur;
-#pragma unroll
-            for (int i = 1; i < n; ++i) trial[i] = eta[i] + t * p[i];
-            KLState<R, n> St;
-            kl_eval<G, R, Model, n>(cf, trial, fp, lane, m, St);
+    for (int i = 0; i < n; ++i) { trial[i] = eta[i]; p[i] = 0; }
+    R gp = 0, t = 1, s_cur = 1;
+    bool have_S = false, done = false, conv = false, in_basin = false;
+    int it = 0, bt = 0;
+    nev = 0;
+    const int max_evals = 1 + fp.n2 * fp.nb;
+    for (int k = 0; k < max_evals; ++k) {
+        if (!__any_sync(wm, !done)) break;
+        KLState<R, n> St;
+        kl_eval<G, R, Model, n>(cf, trial, fp, lane, m, St);
+        if (!done) {
             nev += 1;
-            const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S.f));
-            const bool ok = r_finite(St.f) &&
-                            ((St.f <= S.f + (R)fp.c1 * t * gp + slack) || !r_finite(S.f) || in_basin);
-            if (ok) {
+            bool accepted;
+            if (!have_S) {
+                accepted = true;
+                have_S = true;
+            } else {
+                const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S.f));
+                accepted = r_finite(St.f) &&
+                           ((St.f <= S.f + (R)fp.c1 * t * gp + slack) || !r_finite(S.f) || in_basin);
+            }
+            if (accepted) {
 #pragma unroll
                 for (int i = 0; i < n; ++i) eta[i] = trial[i];
                 S = St;
-                accepted = true;
-                break;
-            }
-            t *= R(0.5);
-        }
-        if (!accepted) break;          // stalled: keep the current iterate
-    }
-    if (!conv) {
-        R gmax = 0;
-        bool gnan = false;
+                R gmax = 0;
+                bool gnan = false;
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-            gmax = r_max(gmax, r_abs(S.g[i]));
-            gnan = gnan || (S.g[i] != S.g[i]);
+                for (int i = 0; i < n; ++i) {
+                    gmax = r_max(gmax, r_abs(S.g[i]));
+                    gnan = gnan || (S.g[i] != S.g[i]);
+                }
+                if (!gnan && gmax <= (R)fp.gtol2) {
+                    conv = true;
+                    done = true;
+                } else if (it >= fp.n2) {
+                    done = true;                   // Newton-step budget exhausted
+                } else {
+                    newton_direction<R, n>(S, fp, p);
+                    gp = 0;
+#pragma unroll
+                    for (int i = 0; i < n; ++i) gp += S.g[i] * p[i];
+                    if (!r_finite(gp)) gp = 0;
+                    s_cur = scale_of<R, n>(eta, fp);
+                    in_basin = !gnan && gmax <= (R)fp.basin;
+                    t = 1;
+                    bt = 0;
+                    it += 1;
+                }
+            } else {
+                t *= R(0.5);
+                bt += 1;
+                if (bt >= fp.nb) done = true;      // stalled: keep the current iterate
+            }
+            if (!done) {
+                trial[0] = eta[0] + t * p[0] * s_cur;
+#pragma unroll
+                for (int i = 1; i < n; ++i) trial[i] = eta[i] + t * p[i];
+            }
         }
-        conv = !gnan && gmax <= (R)fp.gtol2;
     }
     converged = conv;
 }

@@ -21,7 +21,19 @@
 
 namespace klhr {
 
-constexpr int kTileChains = 32;
+// chains per octet per draw (passes of the D-phase); a warp owns 4 * kTilePasses chains
+#ifndef KLHR_TILE_PASSES
+#define KLHR_TILE_PASSES 8
+#endif
+#ifndef KLHR_TILE_MINCTAS
+#define KLHR_TILE_MINCTAS 16
+#endif
+#ifndef KLHR_TILE_W_SMEM
+#define KLHR_TILE_W_SMEM 1
+#endif
+constexpr int kTilePasses = KLHR_TILE_PASSES;
+constexpr int kTileChains = 4 * kTilePasses;
+constexpr int kWarp = 32;
 
 // per-draw scalar variates of one chain (slots 0..2), computed by the owning thread
 template <typename R>
@@ -47,7 +59,7 @@ __device__ __forceinline__ void chain_scalars(uint32_t c0, uint32_t c1, uint32_t
 }
 
 template <typename R, bool kScaled, typename XT, bool kReplay>
-__global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __grid_constant__ StepArgs a) {
     using Model = DiagNormal<R, kScaled>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.mp.D;
@@ -60,7 +72,7 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
     // resident in one wave, so the stored direction-mean columns go to shared memory only when
     // they fit that budget (n_sm = a.tile_mean_smem columns), otherwise they are read from global.
     R* s_w = reinterpret_cast<R*>(smem_raw);
-    XT* xs = reinterpret_cast<XT*>(s_w + ((D + 1) & ~1));
+    XT* xs = reinterpret_cast<XT*>(s_w + (KLHR_TILE_W_SMEM ? ((D + 1) & ~1) : 0));
     float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);
     const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
@@ -71,18 +83,19 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
 
     const long long tile0 = (long long)blockIdx.x * kTileChains;
     const long long c_own = tile0 + 4 * j + o;           // the chain this thread owns in the fit phase
-    const bool own_valid = c_own < a.B;
+    const bool own_valid = j < kTilePasses && c_own < a.B;
     R* g_theta = reinterpret_cast<R*>(a.theta);
     const R* g_w = reinterpret_cast<const R*>(a.mp.p0);
 
-    for (int i = L; i < D; i += kTileChains) s_w[i] = kScaled ? g_w[i] : R(1);
+    if (KLHR_TILE_W_SMEM)
+        for (int i = L; i < D; i += kWarp) s_w[i] = kScaled ? g_w[i] : R(1);
     if constexpr (!kReplay) {
         const R* g_sd = reinterpret_cast<const R*>(a.dir.sd);
-        for (int i = L; i < D; i += kTileChains) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
+        for (int i = L; i < D; i += kWarp) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
         if (n_cols > 1)
-            for (int i = L; i < n_cols; i += kTileChains) s_cdf[i] = (float)reinterpret_cast<const R*>(a.dir.cdf)[i];
+            for (int i = L; i < n_cols; i += kWarp) s_cdf[i] = (float)reinterpret_cast<const R*>(a.dir.cdf)[i];
         if (mean_in_smem)
-            for (int i = L; i < n_stored * D; i += kTileChains) s_mean[i] = (float)g_mean[i];
+            for (int i = L; i < n_stored * D; i += kWarp) s_mean[i] = (float)g_mean[i];
     }
     __syncwarp();
 
@@ -117,13 +130,13 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
         R cp_next = oct_bcast(c_pend, 0, om);
         int col_next = oct_bcast(jcol, 0, om);
 #pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
+        for (int p = 0; p < kTilePasses; ++p) {
             const int cs = 4 * p + o;
             const long long c = tile0 + cs;
             const R cp = cp_next;                          // pending move of this pass's chain
             const int col = col_next;
-            cp_next = oct_bcast(c_pend, (p + 1) & 7, om);  // fetched one pass ahead: hides the shuffle latency
-            col_next = oct_bcast(jcol, (p + 1) & 7, om);
+            cp_next = oct_bcast(c_pend, (p + 1) % kTilePasses, om);  // one pass ahead: hides the shuffle latency
+            col_next = oct_bcast(jcol, (p + 1) % kTilePasses, om);
             if (c >= a.B) continue;                       // octet-uniform
             if (last && cp == R(0)) continue;
             R* row = g_theta + c * D;
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
                         const bool live = i < D;
                         th[s] = live ? row[i] : R(0);
                         xo[s] = (pend && live) ? xr[i] : XT(0);
-                        wv[s] = live ? s_w[i] : R(0);
+                        wv[s] = live ? (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp)) : R(0);
                         if constexpr (!kReplay) {
                             sdv[s] = live ? s_sd[i] : 0.0f;
                             mv[s] = (live && has_mean) ? (mean_in_smem ? mcol_s[i] : (float)__ldg(mcol_g + i)) : 0.0f;
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(kTileChains, 16) tile_kernel(const __grid_cons
             c_pend = 0;
         }
         if (a.tr.rho) {                                   // emit rho = x * inv (test / debugging path)
-            for (int p = 0; p < 8; ++p) {
+            for (int p = 0; p < kTilePasses; ++p) {
                 const int cs = 4 * p + o;
                 const long long c = tile0 + cs;
                 const R ip = oct_bcast(inv, p, om);
@@ -274,10 +287,11 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
     a.Dpad = pad_dim(a.mp.D, xbytes);
     const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
-    size_t smem = (size_t)((a.mp.D + 1) & ~1) * sizeof(R) + (size_t)kTileChains * a.Dpad * xbytes +
+    size_t smem = (KLHR_TILE_W_SMEM ? (size_t)((a.mp.D + 1) & ~1) * sizeof(R) : 0) + (size_t)kTileChains * a.Dpad * xbytes +
                   (size_t)(a.mp.D + n_cols) * sizeof(float);
-    // budget for 14 CTAs per SM: (228 KB / 14) minus the 1 KB the driver reserves per CTA
-    const size_t budget = 228 * 1024 / 14 - 1024;
+    // budget per CTA so that all tiles of B = 65 536 are resident at once: 14 CTAs per SM with
+    // 32-chain tiles, 28 with 16-chain tiles; minus the 1 KB the driver reserves per CTA
+    const size_t budget = 228 * 1024 / (kTilePasses == 8 ? 14 : 28) - 1024;
     const size_t mean_bytes = (size_t)n_stored * a.mp.D * sizeof(float);
     a.tile_mean_smem = (n_stored > 0 && smem + mean_bytes <= budget) ? 1 : 0;
     if (a.tile_mean_smem) smem += mean_bytes;
@@ -294,9 +308,9 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
         e = cudaFuncGetAttributes(&fa, fn);
         if (e != cudaSuccess) return (int)e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kTileChains, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kWarp, smem);
         if (e != cudaSuccess) return (int)e;
-        info->threads = kTileChains;
+        info->threads = kWarp;
         info->smem = (int)smem;
         info->regs = fa.numRegs;
         info->ctas_per_sm = nb;
@@ -305,7 +319,7 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
     const long long grid = (a.B + kTileChains - 1) / kTileChains;
     if (grid <= 0) return 0;
     void* kargs[] = {(void*)&a};
-    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kTileChains), kargs, smem, st);
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kWarp), kargs, smem, st);
     return (int)e;
 }
 

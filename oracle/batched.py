@@ -236,6 +236,7 @@ def _chol_solve(H, g, n):
     Written entry by entry (n = 2 or 4) so the CUDA code can mirror the operation order."""
     B = H.shape[0]
     L = np.zeros_like(H)
+    iL = np.zeros((B, n))
     ok = np.ones(B, dtype=bool)
     with np.errstate(all="ignore"):
         for j in range(n):
@@ -245,23 +246,24 @@ def _chol_solve(H, g, n):
             ok &= acc > 0
             ljj = np.sqrt(np.where(acc > 0, acc, 1.0))
             L[:, j, j] = ljj
+            iL[:, j] = 1.0 / ljj                    # one division per pivot, products elsewhere
             for i in range(j + 1, n):
                 acc = H[:, i, j].copy()
                 for k in range(j):
                     acc = acc - L[:, i, k] * L[:, j, k]
-                L[:, i, j] = acc / ljj
+                L[:, i, j] = acc * iL[:, j]
         yv = np.zeros((B, n))
         for i in range(n):
             acc = -g[:, i]
             for k in range(i):
                 acc = acc - L[:, i, k] * yv[:, k]
-            yv[:, i] = acc / L[:, i, i]
+            yv[:, i] = acc * iL[:, i]
         p = np.zeros((B, n))
         for i in reversed(range(n)):
             acc = yv[:, i].copy()
             for k in range(i + 1, n):
                 acc = acc - L[:, k, i] * p[:, k]
-            p[:, i] = acc / L[:, i, i]
+            p[:, i] = acc * iL[:, i]
     ok &= np.all(np.isfinite(p), axis=1)
     return p, ok
 

@@ -26,9 +26,10 @@ def _run(name, dtype, force_octet=False):
     return t, gpu, ref, rel_errors(gpu, ref, meta["family"])
 
 
-# the diagonal-Gaussian tapes go through the tile kernel by default; "octet" forces the
-# general kernel so that both device paths are held to the same bar
-KERNELS = [(n, False) for n in GAUSS_TAPES] + [(n, True) for n in GAUSS_TAPES[:4]]
+# by default the diagonal-Gaussian tapes go through the tile kernel and everything else through
+# the chain kernel (thread-per-chain fit); force_octet selects the general octet kernel, so all
+# three device paths are held to the same bar
+KERNELS = [(n, False) for n in GAUSS_TAPES] + [(n, True) for n in GAUSS_TAPES]
 
 
 @pytest.mark.parametrize("name,force_octet", KERNELS)
@@ -54,9 +55,10 @@ def test_gauss_family_fp32_1e4(name, force_octet):
     assert (gpu["accept"] != ref["accept"]).mean() <= 0.002
 
 
+@pytest.mark.parametrize("force_octet", [False, True])
 @pytest.mark.parametrize("name", SINH_TAPES)
-def test_sinh_family_fp64(name):
-    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float64)
+def test_sinh_family_fp64(name, force_octet):
+    t, gpu, ref, (em, es, ez, er) = _run(name, torch.float64, force_octet)
     conv = ref["converged"]
     worst = np.maximum.reduce([em, es, ez])
     # converged fits are reproduced to 1e-10; fits that exhaust the iteration budget sit on

@@ -30,8 +30,10 @@ def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, dire
 @pytest.mark.parametrize("model_name,data,family,force_octet", [
     ("ill-normal", {"D": 100}, "gauss", False), ("ill-normal", {"D": 100}, "gauss", True),
     ("normal", {"D": 300}, "gauss", False), ("normal", {"D": 5}, "gauss", False),
-    ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 1}, "sinh", False),
-    ("rosenbrock", {"D": 2}, "gauss", False), ("ar1", {"N": 20}, "gauss", False)])
+    ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 4}, "gauss", True),
+    ("funnel", {"D": 1}, "sinh", False), ("funnel", {"D": 1}, "sinh", True),
+    ("rosenbrock", {"D": 2}, "gauss", False), ("ar1", {"N": 20}, "gauss", False),
+    ("ar1", {"N": 150}, "gauss", False), ("normal", {"D": 3}, "sinh", False)])
 def test_free_running_step_equals_oracle_on_emitted_variates(model_name, data, family, force_octet):
     """The free-running kernel emits the direction and variates it drew; replaying them through
     the oracle must give the same fit, proposal, ratio, flag and state (fp64, 1e-10)."""

@@ -19,7 +19,8 @@ ap.add_argument("--direction", action="store_true", help="eigen_method_one law: 
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 dt = torch.float64 if a.dtype == "f64" else torch.float32
-model = kb.BSModel(stan_file=f"stan/{a.model}.stan", data=json.loads(a.data), device=dev)
+data = json.load(open(a.data[1:])) if a.data.startswith("@") else json.loads(a.data)
+model = kb.BSModel(stan_file=f"stan/{a.model}.stan", data=data, device=dev)
 base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48) if a.family == "sinh" else dict(family="gauss")
 fit = kb.FitConfig(**base).for_dtype(dt)
 fit.force_octet = a.octet
