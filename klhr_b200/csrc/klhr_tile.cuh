@@ -154,22 +154,18 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (g0 + 16 * h >= D) break;          // octet-uniform: no live element in this half
-                    // 1. issue every load of the half first (theta slice from L2, previous x, weights,
-                    //    direction scales); their latency hides behind the RNG arithmetic of step 2
-                    R th[8], wv[8];
+                    // 1. issue the long-latency loads of the half first (theta slice from L2, previous x);
+                    //    they hide behind the RNG arithmetic of step 2.  Weights, scales and means are
+                    //    read from shared memory at the point of use: preloading them too needs more
+                    //    than 128 registers and the spills cost more than the short-scoreboard waits.
+                    R th[8];
                     XT xo[8];
-                    float sdv[8], mv[8];
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
                         const int i = g0 + j + 8 * (2 * h + (s >> 2)) + 32 * (s & 3);
                         const bool live = i < D;
                         th[s] = live ? row[i] : R(0);
                         xo[s] = (pend && live) ? xr[i] : XT(0);
-                        wv[s] = live ? (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp)) : R(0);
-                        if constexpr (!kReplay) {
-                            sdv[s] = live ? s_sd[i] : 0.0f;
-                            mv[s] = (live && has_mean) ? (mean_in_smem ? mcol_s[i] : (float)__ldg(mcol_g + i)) : 0.0f;
-                        }
                     }
                     // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
                     float z[8];
@@ -201,13 +197,14 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                                     x = reinterpret_cast<const R*>(a.rho)[c * D + i];
                                     xr[i] = (XT)x;
                                 } else {
-                                    const float xf = fmaf(sdv[s], z[s], mv[s]);
+                                    const float mvs = has_mean ? (mean_in_smem ? mcol_s[i] : (float)__ldg(mcol_g + i)) : 0.0f;
+                                    const float xf = fmaf(s_sd[i], z[s], mvs);
                                     xr[i] = (XT)xf;
                                     x = (R)xf;
                                 }
                                 const R xt = x + tol;
                                 ss += xt * xt;
-                                const R xw = x * wv[s];
+                                const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
                                 sA += x * xw;
                                 sB += t0 * xw;
                             }
