@@ -1,0 +1,97 @@
+// klhr_b200 -- CTA-cooperative dense quadratic forms on the FP64 tensor cores.
+//
+// stan/corr-normal.stan has a dense precision P (D x D, shared by all chains); the line
+// restriction needs A = rho^T P rho and Bq = -theta^T P rho for every chain and draw, i.e. the
+// row-wise products of the CTA's rho tile with P: V = R P (chains x D), a small GEMM.  Doing it
+// per chain (CorrNormal::setup) re-reads all of P for every chain; here the CTA's warps split
+// the columns of P, every element of P is loaded once per CTA and draw, and the products run on
+// mma.sync.m8n8k4.f64 (DMMA).  V never leaves registers: each lane folds its 8x8 accumulator
+// fragments straight into partial sums of rho.V and theta.V.
+#pragma once
+#include "klhr_common.cuh"
+
+namespace klhr {
+
+constexpr int kDenseMaxChains = 16;      // two m8 tiles per warp
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// th_tile / rh_tile: [cpb][Dpad] rows in shared memory (rows of absent chains must be zero).
+// red: [n_warps][16][2] scratch.  Every thread of the CTA must call this (it synchronises).
+// Returns A and Bq of chain `o` (octet-uniform).
+__device__ inline void dense_cta_quadratic(const double* th_tile, const double* rh_tile, const double* __restrict__ P,
+                                           int D, int Dpad, int cpb, double (*red)[kDenseMaxChains][2], int o,
+                                           double& A_out, double& Bq_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int r8 = lane >> 2, k4 = lane & 3;          // fragment coordinates
+    __syncthreads();                                   // rho / theta rows of every chain are in place
+    double pa[2] = {0, 0}, pb[2] = {0, 0};
+    const int n_tiles = (D + 7) >> 3;
+    for (int chunk = 0; chunk * 8 * n_warps < n_tiles; ++chunk) {
+        // this warp's up to 8 column tiles of the chunk: nt = (chunk * 8 + q) * n_warps + warp
+        double acc[2][8][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
+        for (int k0 = 0; k0 < D; k0 += 4) {
+            const int k = k0 + k4;
+            const bool kin = k < D;
+            const double a0 = (kin && r8 < cpb) ? rh_tile[(size_t)r8 * Dpad + k] : 0.0;
+            const double a1 = (kin && 8 + r8 < cpb) ? rh_tile[(size_t)(8 + r8) * Dpad + k] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int nt = (chunk * 8 + q) * n_warps + warp;
+                const int n = nt * 8 + r8;             // B fragment: row k4, column r8 of the tile
+                const double b = (kin && n < D) ? __ldg(P + (size_t)k * D + n) : 0.0;
+                dmma_m8n8k4(acc[0][q][0], acc[0][q][1], a0, b);
+                dmma_m8n8k4(acc[1][q][0], acc[1][q][1], a1, b);
+            }
+        }
+        // C fragment: row r8, columns 2*k4 + {0,1} of tile nt.  Fold V into rho.V and theta.V.
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int nt = (chunk * 8 + q) * n_warps + warp;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = nt * 8 + 2 * k4 + e;
+                if (n < D) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int row = 8 * m + r8;
+                        if (row < cpb) {
+                            const double v = acc[m][q][e];
+                            pa[m] += rh_tile[(size_t)row * Dpad + n] * v;
+                            pb[m] -= th_tile[(size_t)row * Dpad + n] * v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {                       // sum over the 4 lanes sharing a row
+        pa[m] += __shfl_xor_sync(0xffffffffu, pa[m], 1);
+        pa[m] += __shfl_xor_sync(0xffffffffu, pa[m], 2);
+        pb[m] += __shfl_xor_sync(0xffffffffu, pb[m], 1);
+        pb[m] += __shfl_xor_sync(0xffffffffu, pb[m], 2);
+        if (k4 == 0) {
+            red[warp][8 * m + r8][0] = pa[m];
+            red[warp][8 * m + r8][1] = pb[m];
+        }
+    }
+    __syncthreads();
+    double A = 0, B = 0;
+    for (int w = 0; w < n_warps; ++w) {                 // fixed order: deterministic
+        A += red[w][o][0];
+        B += red[w][o][1];
+    }
+    A_out = A;
+    Bq_out = B;
+    __syncthreads();                                    // red may be rewritten by the next draw
+}
+
+}  // namespace klhr

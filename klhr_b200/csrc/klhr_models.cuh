@@ -39,6 +39,7 @@ __device__ __forceinline__ Jet<R> quad_eval(const QuadCoef<R>& c, R y) {
 // ---- stan/normal.stan:1-9 and stan/ill-normal.stan:1-12  (diagonal Gaussian)
 template <typename R, bool kScaled>
 struct DiagNormal {
+    static constexpr bool kDenseCta = false;
     using Coef = QuadCoef<R>;
     __device__ static __forceinline__ R wgt(int i, const ModelParams& mp) {
         return kScaled ? __ldg(reinterpret_cast<const R*>(mp.p0) + i) : R(1);
@@ -70,6 +71,7 @@ struct DiagNormal {
 // ---- stan/corr-normal.stan:1-20  (dense precision P = Sigma^-1, symmetric)
 template <typename R>
 struct CorrNormal {
+    static constexpr bool kDenseCta = true;     // fp64: CTA-cooperative DMMA path, klhr_dense.cuh
     using Coef = QuadCoef<R>;
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const R* P = reinterpret_cast<const R*>(mp.p0);
@@ -104,6 +106,7 @@ struct CorrNormal {
 // ---- stan/ar1.stan:1-14   e_t(v) = v_t - alpha v_{t-1}
 template <typename R>
 struct AR1 {
+    static constexpr bool kDenseCta = false;
     using Coef = QuadCoef<R>;
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const R al = (R)mp.s0, ib2 = (R)mp.s1;
@@ -149,6 +152,7 @@ struct AR1 {
 // ---- stan/funnel.stan:1-11   params [x, alpha_1..alpha_Da]
 template <typename R>
 struct Funnel {
+    static constexpr bool kDenseCta = false;
     struct Coef { R x0, r0, a0, a1, a2, hd, l0; };
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         R a0 = 0, a1 = 0, a2 = 0;
@@ -197,6 +201,7 @@ struct Funnel {
 // ---- stan/rosenbrock.stan:1-12   params [v_1..v_Dh, t_1..t_Dh]
 template <typename R>
 struct Rosenbrock {
+    static constexpr bool kDenseCta = false;
     struct Coef { R b1, b2, b3, b4; };      // l(y) - l(0) = b1 y + b2 y^2 + b3 y^3 + b4 y^4
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const int Dh = mp.i0;
@@ -247,6 +252,7 @@ struct Rosenbrock {
 // over t = K+1..T, packed [G (K+1)^2 | c (K+1) | yy].  sum r^2 = yy - 2 phi.c + phi^T G phi.
 template <typename R>
 struct ARK {
+    static constexpr bool kDenseCta = false;
     struct Coef { R p0, p1, p2, q0, q1, q2, u0, ru, nm1, l0; };
     __device__ static __forceinline__ void gram_forms(const R* th, const R* rh, int lane, unsigned m,
                                                       const ModelParams& mp, R& q0, R& q1, R& q2,

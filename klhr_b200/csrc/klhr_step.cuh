@@ -14,6 +14,7 @@
 #pragma once
 #include "klhr_fit.cuh"
 #include "klhr_models.cuh"
+#include "klhr_dense.cuh"
 
 namespace klhr {
 
@@ -76,6 +77,10 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
     R* s_mean = shared_tail + D;                       // [n_cols][D]
     R* s_shift = s_mean + (size_t)(kReplay ? 0 : (a.dir.mean_cols ? a.dir.n_cols : 0)) * D;   // [D]
     __shared__ unsigned long long cta_evals;
+    // dense targets in fp64: line coefficients for all chains of the CTA at once on the FP64
+    // tensor cores (klhr_dense.cuh); every thread takes part, so the draw loop runs CTA-uniform
+    constexpr bool kDense = Model::kDenseCta && sizeof(R) == 8;
+    __shared__ double dense_red[kDense ? 8 : 1][kDenseMaxChains][2];
 
     const long long c = (long long)blockIdx.x * cpb + o;
     const bool valid = c < a.B;
@@ -98,6 +103,8 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
             th[i] = g_theta[c * D + i];
             if constexpr (kAccum) { a1[i] = 0; a2[i] = 0; }
         }
+    } else if (kDense) {
+        for (int i = lane; i < D; i += kOct) { th[i] = 0; rh[i] = 0; }
     }
     __syncthreads();
 
@@ -106,10 +113,11 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
     const R tol = (R)a.fp.tol;
     const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
 
-    if (valid) {
+    {
         for (int step = 0; step < a.n_steps; ++step) {
             const long long row = (long long)step * a.B + c;      // trace row
-            R z_init, z_prop, u, init2 = 0, init3 = 0;
+            R z_init = 0, z_prop = 0, u = 0, init2 = 0, init3 = 0;
+            if (valid) {
             // ---------------------------------------------------------------- 1. direction
             if constexpr (kReplay) {
                 const R* g_rho = reinterpret_cast<const R*>(a.rho);
@@ -214,8 +222,19 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
                 R* g = reinterpret_cast<R*>(a.tr.rho) + row * D;
                 for (int i = lane; i < D; i += kOct) g[i] = rh[i];
             }
+            }   // valid
             // ---------------------------------------------------------------- 2. line setup
-            const typename Model::Coef cf = Model::setup(th, rh, lane, om, a.mp);
+            typename Model::Coef cf;
+            if constexpr (kDense) {
+                double A, Bq;
+                dense_cta_quadratic(reinterpret_cast<const double*>(sm), reinterpret_cast<const double*>(sm) + (size_t)cpb * Dpad,
+                                    reinterpret_cast<const double*>(a.mp.p0), D, Dpad, cpb, dense_red, o, A, Bq);
+                cf.A = (R)A;
+                cf.Bq = (R)Bq;
+            } else {
+                if (valid) cf = Model::setup(th, rh, lane, om, a.mp);
+            }
+            if (!valid) continue;
             // ---------------------------------------------------------------- 3.+4. fit, propose, MH
             StepOut<R> so;
             fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so);
@@ -256,6 +275,8 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
                 }
             }
         }
+    }
+    if (valid) {
         // ------------------------------------------------------------------ write back
         for (int i = lane; i < D; i += kOct) g_theta[c * D + i] = th[i];
         if (lane == 0) {
@@ -326,10 +347,10 @@ struct LaunchPlan {
     size_t smem;
 };
 
-inline LaunchPlan plan_step(int D, int real_bytes, bool accum, int n_cols, bool replay) {
+inline LaunchPlan plan_step(int D, int real_bytes, bool accum, int n_cols, bool replay, int max_threads = kThreadsMax) {
     const int Dpad = pad_dim(D, real_bytes);
     LaunchPlan p;
-    for (int threads = kThreadsMax; threads >= 32; threads /= 2) {
+    for (int threads = max_threads; threads >= 32; threads /= 2) {
         const int cpb = threads / kOct;
         const size_t rows = (size_t)(accum ? 4 : 2) * cpb;
         const size_t tail = (size_t)D * (1 + (replay ? 0 : n_cols) + 1);
@@ -346,7 +367,8 @@ int launch_step_typed(const StepArgs& args_in, int family, bool replay, bool acc
                       LaunchInfo* info) {
     StepArgs a = args_in;
     const int n_cols = a.dir.mean_cols ? a.dir.n_cols : 0;
-    const LaunchPlan p = plan_step(a.mp.D, (int)sizeof(R), accum, n_cols, replay);
+    const LaunchPlan p = plan_step(a.mp.D, (int)sizeof(R), accum, n_cols, replay,
+                                   (Model::kDenseCta && sizeof(R) == 8) ? 8 * kDenseMaxChains : kThreadsMax);
     if (p.smem > 227 * 1024) return -20;
     a.Dpad = pad_dim(a.mp.D, (int)sizeof(R));
     const void* fn = nullptr;
