@@ -77,8 +77,10 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
 // The tile kernel covers: diagonal-Gaussian targets, Gaussian family, no in-kernel accumulators
 // and no thinned-draw output.  Everything else runs on the general octet kernel.
 static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
+    // at most 2 stored direction-mean columns: they live in the tile's shared memory (J = 2 default)
+    const int n_stored = a.dir.mean_cols ? a.dir.n_cols - a.dir.n_zero_cols : 0;
     return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && !a.acc.draws &&
-           (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && a.fp.N <= kMaxNodes;
+           (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && n_stored <= 2;
 }
 
 // The chain kernel (thread-per-chain fit, model-generic line setup) covers every target and both

@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
                 const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
                 const R* mcol = col < n_stored ? s_mean + (size_t)col * D : nullptr;
                 R ss = 0;
-                // element i = g0 + j + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128), word r
+                // element i = g0 + j + 32 t + 8 r  <->  Philox slot kSlotDir + j + 8 t + g0 / 4, word r
                 for (int g0 = 0; g0 < D; g0 += 128) {
-                    for (int t = 0; t < 4 && g0 + 8 * t < D; ++t) {
+                    for (int t = 0; t < 4 && g0 + 32 * t < D; ++t) {
                         uint32_t w[4];
                         Philox::block(c0, c1, d0, kSlotDir + (uint32_t)(j + 8 * t) + (uint32_t)(g0 / 4), k0, k1d, w);
                         float z[4];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
                         box_muller_f32(w[2], w[3], z[2], z[3]);
 #pragma unroll
                         for (int rr = 0; rr < 4; ++rr) {
-                            const int i = g0 + j + 8 * t + 32 * rr;
+                            const int i = g0 + j + 32 * t + 8 * rr;
                             if (i < D) {
                                 const R x = (R)fmaf((float)s_sd[i], z[rr], mcol ? (float)mcol[i] : 0.0f);
                                 rh[i] = x;

@@ -135,7 +135,7 @@ constexpr uint32_t kSlotScalarA = 0;   // w0: direction-column uniform; w2,w3: z
 constexpr uint32_t kSlotProposal = 1;  // w0..w3: two 53-bit uniforms -> Box-Muller -> z_prop
 constexpr uint32_t kSlotAccept = 2;    // w0,w1: 53-bit accept uniform
 constexpr uint32_t kSlotInit4 = 3;     // w0..w3: two Box-Muller pairs -> init4[2], init4[3] (sinh)
-constexpr uint32_t kSlotDir = 8;       // element i of the direction: slot kSlotDir + (i % 32) + 32 (i / 128), word (i / 32) % 4
+constexpr uint32_t kSlotDir = 8;       // direction element i: slot kSlotDir + (i % 8) + 8 ((i % 128) / 32) + 32 (i / 128), word (i % 32) / 8
 
 // uniform in (0,1) from 32 bits: (x + 0.5) / 2^32
 __device__ __forceinline__ float u01_32(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }

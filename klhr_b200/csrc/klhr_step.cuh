@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
                     mcol = j < a.dir.n_cols - a.dir.n_zero_cols ? s_mean + (size_t)j * D : nullptr;   // zero column
                 }
                 R ss = 0;
-                // element i = g0 + lane + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128),
+                // element i = g0 + lane + 32 t + 8 r  <->  Philox slot kSlotDir + lane + 8 t + g0 / 4,
                 // word r; x is formed in fp32 (same stream and rounding as the tile kernel)
                 for (int g0 = 0; g0 < D; g0 += 128) {
-                    for (int t = 0; t < 4 && g0 + 8 * t < D; ++t) {
+                    for (int t = 0; t < 4 && g0 + 32 * t < D; ++t) {
                         uint32_t w[4];
                         Philox::block(c0, c1, d0, kSlotDir + (uint32_t)(lane + 8 * t) + (uint32_t)(g0 / 4), k0, k1d, w);
                         float z[4];
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
                         box_muller_f32(w[2], w[3], z[2], z[3]);
 #pragma unroll
                         for (int rr = 0; rr < 4; ++rr) {
-                            const int i = g0 + lane + 8 * t + 32 * rr;
+                            const int i = g0 + lane + 32 * t + 8 * rr;
                             if (i < D) {
                                 const R x = (R)fmaf((float)s_sd[i], z[rr], mcol ? (float)mcol[i] : 0.0f);
                                 rh[i] = x;

@@ -17,6 +17,7 @@
 // Variate streams are the same function of (seed, chain, draw, element) as in the octet
 // kernel, so both kernels produce the same chains up to fp32 rounding of the direction.
 #pragma once
+#include <type_traits>
 #include "klhr_step.cuh"
 
 namespace klhr {
@@ -78,7 +79,6 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     float* s_cdf = s_sd + D;
     float* s_mean = s_cdf + n_cols;
-    const bool mean_in_smem = a.tile_mean_smem != 0;
     const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
 
     const long long tile0 = (long long)blockIdx.x * kTileChains;
@@ -94,8 +94,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
         for (int i = L; i < D; i += kWarp) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
         if (n_cols > 1)
             for (int i = L; i < n_cols; i += kWarp) s_cdf[i] = (float)reinterpret_cast<const R*>(a.dir.cdf)[i];
-        if (mean_in_smem)
-            for (int i = L; i < n_stored * D; i += kWarp) s_mean[i] = (float)g_mean[i];
+        for (int i = L; i < n_stored * D; i += kWarp) s_mean[i] = (float)g_mean[i];
     }
     __syncwarp();
 
@@ -142,74 +141,80 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
             R* row = g_theta + c * D;
             XT* xr = xs + (size_t)cs * Dx;
             const bool has_mean = col < n_stored;         // a zero column (klhr.py:64-66) is not stored
-            const R* mcol_g = g_mean + (size_t)(has_mean ? col : 0) * D;
             const float* mcol_s = s_mean + (size_t)(has_mean ? col : 0) * D;
             const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
             const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
             const bool pend = cp != R(0);
             R ss = 0, sA = 0, sB = 0;
-            // element i = g0 + j + 8 t + 32 r  <->  Philox slot kSlotDir + (i % 32) + 32 (i / 128), word r.
-            // Each half handles blocks t = 2h, 2h+1 (8 elements per lane).
-            for (int g0 = 0; g0 < D; g0 += 128) {
+            // Element i = g0 + j + 8 s, slot s = 4 t + r of this lane  <->  Philox counter slot
+            // kSlotDir + j + 8 t + g0 / 4, word r.  A half handles slots 8h..8h+7 (blocks 2h, 2h+1).  When
+            // the half is FULL (every slot live for every lane) the body carries no predicates at all;
+            // only the last, partial half pays for bounds checks and skips its dead slots.
+            auto do_half = [&](auto full_tag, const int g0, const int h) {
+                constexpr bool kFull = decltype(full_tag)::value;
+                // 1. issue the long-latency loads first (theta slice from L2, previous x); they hide
+                //    behind the RNG arithmetic of step 2.  Weights, scales and means are read from
+                //    shared memory at the point of use (preloading them needs > 128 registers).
+                R th[8];
+                XT xo[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (g0 + 16 * h >= D) break;          // octet-uniform: no live element in this half
-                    // 1. issue the long-latency loads of the half first (theta slice from L2, previous x);
-                    //    they hide behind the RNG arithmetic of step 2.  Weights, scales and means are
-                    //    read from shared memory at the point of use: preloading them too needs more
-                    //    than 128 registers and the spills cost more than the short-scoreboard waits.
-                    R th[8];
-                    XT xo[8];
+                for (int s = 0; s < 8; ++s) {
+                    const int i = g0 + j + 8 * (8 * h + s);
+                    const bool live = kFull || i < D;
+                    th[s] = live ? row[i] : R(0);
+                    xo[s] = (pend && live) ? xr[i] : XT(0);
+                }
+                // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
+                float z[8];
+                if constexpr (!kReplay) {
+                    if (!last) {
+                        uint32_t w[2][4];
+                        Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
+                                          k0, k1d, w);
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int i = g0 + j + 8 * (2 * h + (s >> 2)) + 32 * (s & 3);
-                        const bool live = i < D;
-                        th[s] = live ? row[i] : R(0);
-                        xo[s] = (pend && live) ? xr[i] : XT(0);
+                        for (int t = 0; t < 2; ++t) {
+                            box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
+                            box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
+                        }
                     }
-                    // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
-                    float z[8];
-                    if constexpr (!kReplay) {
+                }
+                // 3. apply the pending move, form the new x and the three sums
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int ib = g0 + 8 * (8 * h + s);
+                    if (!kFull && ib >= D) continue;      // warp-uniform: dead slot of the partial half
+                    const int i = ib + j;
+                    if (kFull || i < D) {
+                        R t0 = th[s];
+                        if (pend) {
+                            t0 = t0 + cp * (R)xo[s];
+                            row[i] = t0;
+                        }
                         if (!last) {
-                            uint32_t w[2][4];
-                            Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
-                                              k0, k1d, w);
-#pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
-                                box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
+                            R x;
+                            if constexpr (kReplay) {
+                                x = reinterpret_cast<const R*>(a.rho)[c * D + i];
+                                xr[i] = (XT)x;
+                            } else {
+                                const float xf = fmaf(s_sd[i], z[s], has_mean ? mcol_s[i] : 0.0f);
+                                xr[i] = (XT)xf;
+                                x = (R)xf;
                             }
+                            const R xt = x + tol;
+                            ss += xt * xt;
+                            const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
+                            sA += x * xw;
+                            sB += t0 * xw;
                         }
                     }
-                    // 3. apply the pending move, form the new x and the three sums
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int i = g0 + j + 8 * (2 * h + (s >> 2)) + 32 * (s & 3);
-                        if (i < D) {
-                            R t0 = th[s];
-                            if (pend) {
-                                t0 = t0 + cp * (R)xo[s];
-                                row[i] = t0;
-                            }
-                            if (!last) {
-                                R x;
-                                if constexpr (kReplay) {
-                                    x = reinterpret_cast<const R*>(a.rho)[c * D + i];
-                                    xr[i] = (XT)x;
-                                } else {
-                                    const float mvs = has_mean ? (mean_in_smem ? mcol_s[i] : (float)__ldg(mcol_g + i)) : 0.0f;
-                                    const float xf = fmaf(s_sd[i], z[s], mvs);
-                                    xr[i] = (XT)xf;
-                                    x = (R)xf;
-                                }
-                                const R xt = x + tol;
-                                ss += xt * xt;
-                                const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
-                                sA += x * xw;
-                                sB += t0 * xw;
-                            }
-                        }
-                    }
+                }
+            };
+            for (int g0 = 0; g0 < D; g0 += 128) {
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    if (g0 + 64 * h >= D) break;          // warp-uniform: nothing left
+                    if (g0 + 64 * h + 63 < D) do_half(std::true_type{}, g0, h);
+                    else do_half(std::false_type{}, g0, h);
                 }
             }
             if (last) continue;
@@ -290,8 +295,9 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
     // 32-chain tiles, 28 with 16-chain tiles; minus the 1 KB the driver reserves per CTA
     const size_t budget = 228 * 1024 / (kTilePasses == 8 ? 14 : 28) - 1024;
     const size_t mean_bytes = (size_t)n_stored * a.mp.D * sizeof(float);
-    a.tile_mean_smem = (n_stored > 0 && smem + mean_bytes <= budget) ? 1 : 0;
-    if (a.tile_mean_smem) smem += mean_bytes;
+    (void)budget;
+    a.tile_mean_smem = n_stored > 0 ? 1 : 0;
+    smem += mean_bytes;
     if (smem > 227 * 1024) return -20;
     const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
                             : (const void*)tile_kernel<R, kScaled, float, false>;
