@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
     long long n_acc = 0;
     unsigned long long n_evals = 0;
 
-    for (int step = 0; step <= a.n_steps; ++step) {
-        const bool last = step == a.n_steps;             // extra pass: only flush pending updates
+    for (int step = 0; step < a.n_steps; ++step) {
+        constexpr bool last = false;                     // (the flush of pending moves is a separate loop below)
         const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
         const uint32_t d0 = (uint32_t)draw, k1d = k1 ^ (uint32_t)(draw >> 32);
         R u_col = 0, z_init = 0, z_prop = 0, u = 0;
@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
             cp_next = oct_bcast(c_pend, (p + 1) % kTilePasses, om);  // one pass ahead: hides the shuffle latency
             col_next = oct_bcast(jcol, (p + 1) % kTilePasses, om);
             if (c >= a.B) continue;                       // octet-uniform
-            if (last && cp == R(0)) continue;
             R* row = g_theta + c * D;
             XT* xr = xs + (size_t)cs * Dx;
             const bool has_mean = col < n_stored;         // a zero column (klhr.py:64-66) is not stored
@@ -270,6 +269,16 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
             }
         }
         __syncwarp();
+    }
+    // ------------------------------------------------------------------------ flush pending moves
+    for (int p = 0; p < kTilePasses; ++p) {
+        const int cs = 4 * p + o;
+        const long long c = tile0 + cs;
+        const R cp = oct_bcast(c_pend, p, om);
+        if (c >= a.B || cp == R(0)) continue;
+        R* row = g_theta + c * D;
+        const XT* xr = xs + (size_t)cs * Dx;
+        for (int i = j; i < D; i += kOct) row[i] = row[i] + cp * (R)xr[i];
     }
     if (own_valid) {
         if (a.acc.accept_count) a.acc.accept_count[c_own] += n_acc;
