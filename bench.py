@@ -309,7 +309,11 @@ def run_b200(args):
         zvar = ((summ["var"] - truth).abs() / summ["mcse_var"]).max()
         ess_min = float(summ["ess"].min())
         ms = a0.elapsed_time(a1)
-        ess = {"min_ess_per_sec": world * ess_min / (ms * 1e-3), "min_ess_per_draw": ess_min / (B * S_ess),
+        # ESS per draw is a property of the chains (both kernels draw the same streams); the pass that
+        # measures it needs per-chain sums and therefore runs on the accumulating octet kernel, so
+        # ESS/sec of the production path = ESS per chain-draw x the timed chain-draws/sec
+        ess = {"min_ess_per_sec": (ess_min / (B * S_ess)) * value, "min_ess_per_draw": ess_min / (B * S_ess),
+               "min_ess_per_sec_of_stats_pass": world * ess_min / (ms * 1e-3),
                "draws_per_chain": S_ess, "estimator": "between-chain variance of chain means, B independent chains",
                "max_abs_z_mean": float(zmean), "max_abs_z_var": float(zvar),
                "acceptance": sampler.acceptance_probability}
@@ -350,8 +354,9 @@ def run_b200(args):
                          "kernel": ("klhr::tile_kernel (csrc/klhr_tile.cuh)" if info["threads"] == 32 else
                                     "klhr::step_kernel (csrc/klhr_step.cuh)"),
                          "algorithmic_bytes_per_chain_draw": bytes_per_draw,
-                         "note": f"{S} draws fused per launch: actual HBM traffic is (2*D*{rb}+16)/{S} B per "
-                                 "chain-draw; achieved counts SURVEY 8(d) algorithmic bytes"},
+                         "note": f"achieved = SURVEY 8(d) algorithmic bytes x chain-draws / launch time; {S} draws are "
+                                 "fused per launch and theta (52 MB) stays L2-resident between draws, so DRAM "
+                                 "traffic (ncu) is far below the algorithmic bytes"},
             "ess": ess,
         }
         if world == 1 and not args.no_cpu_baseline:
