@@ -66,6 +66,8 @@ typedef struct klhr_fit {
     int32_t n_nodes;             /* N, Gauss-Hermite nodes (<= KLHR_MAX_NODES)            */
     int32_t n1, n2, nb;          /* stage-1 iterations, stage-2 Newton steps, halvings    */
     int32_t flags;               /* KLHR_FIT_* bits                                        */
+    int32_t kmax;                /* cap on stage-2 KL evaluations per fit (<= 0: 1 + n2*nb) */
+    int32_t reserved;
     double initscale;            /* klhr.py:24                                            */
     double tol;                  /* klhr.py:28 / klhr_sinh.py:26                          */
     double scale_clip;           /* klhr.py:30 / klhr_sinh.py:28                          */

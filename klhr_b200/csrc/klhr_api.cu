@@ -64,6 +64,7 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     if (f->n_nodes < 1 || f->n_nodes > KLHR_MAX_NODES) return fail(-7, "n_nodes out of range");
     if (f->n1 < 0 || f->n2 < 0 || f->nb < 1) return fail(-8, "iteration budgets out of range");
     fp.family = f->family; fp.N = f->n_nodes; fp.n1 = f->n1; fp.n2 = f->n2; fp.nb = f->nb;
+    fp.kmax = (f->kmax > 0 && f->kmax < 1 + f->n2 * f->nb) ? f->kmax : 1 + f->n2 * f->nb;
     fp.initscale = f->initscale; fp.tol = f->tol; fp.scale_clip = f->scale_clip;
     fp.gtol1 = f->gtol1; fp.gtol2 = f->gtol2; fp.step_cap = f->step_cap; fp.c1 = f->c1; fp.basin = f->basin;
     for (int i = 0; i < kMaxNodes; ++i) {

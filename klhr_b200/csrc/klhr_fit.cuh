@@ -19,6 +19,7 @@ struct FitParams {
     int family;            // KLHR_FAMILY_GAUSS | KLHR_FAMILY_SINH
     int N;                 // quadrature nodes (<= kMaxNodes)
     int n1, n2, nb;        // stage-1 iterations, stage-2 Newton steps, halvings per step
+    int kmax;              // cap on stage-2 KL evaluations
     double initscale, tol, scale_clip;
     double gtol1, gtol2, step_cap, c1, basin;
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
@@ -331,9 +332,10 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
     for (int i = 0; i < n; ++i) { trial[i] = eta[i]; p[i] = 0; }
     R gp = 0, t = 1, s_cur = 1;
     bool have_S = false, done = false, conv = false, in_basin = false;
-    int it = 0, bt = 0;
+    int it = 0, bt = 0, slow = 0;
+    R g_prev = Num<R>::inf();
     nev = 0;
-    const int max_evals = 1 + fp.n2 * fp.nb;
+    const int max_evals = fp.kmax;
     for (int k = 0; k < max_evals; ++k) {
         if (!__any_sync(wm, !done)) break;
         KLState<R, n> St;
@@ -360,12 +362,17 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
                     gmax = r_max(gmax, r_abs(S.g[i]));
                     gnan = gnan || (S.g[i] != S.g[i]);
                 }
+                // flat valley: inside the basin a Newton step must at least halve the gradient; two in
+                // a row that do not -> stop (see oracle/batched.py:stage2_newton)
+                const bool lag = in_basin && !(gmax <= R(0.5) * g_prev);
+                slow = lag ? slow + 1 : 0;
                 if (!gnan && gmax <= (R)fp.gtol2) {
                     conv = true;
                     done = true;
-                } else if (it >= fp.n2) {
-                    done = true;                   // Newton-step budget exhausted
+                } else if (it >= fp.n2 || slow >= 2) {
+                    done = true;                   // Newton-step budget exhausted, or flat valley
                 } else {
+                    g_prev = gmax;
                     newton_direction<R, n>(S, fp, p);
                     gp = 0;
 #pragma unroll

@@ -39,6 +39,7 @@ class FitConfig:
     n1: int = 12
     n2: int = 24
     nb: int = 8
+    kmax: int = 0                      # cap on stage-2 KL evaluations (0: 1 + n2 * nb)
     gtol1: float = 1e-8
     gtol2: float = 1e-10
     step_cap: float = 2.0
@@ -68,7 +69,7 @@ class FitConfig:
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin, flags=1 if self.force_octet else 0)
+                         basin=self.basin, flags=1 if self.force_octet else 0, kmax=int(self.kmax))
         for i in range(self.N):
             d.x[i] = float(self.x[i])
             d.w[i] = float(self.w[i])

@@ -51,7 +51,8 @@ class KLHR(MCMCBase):
         budget = dict(fit_budget or {})
         self._fit = engine.FitConfig(family=self._family, N=N, initscale=initscale, tol=tol,
                                      scale_clip=float(scale_clip), x=self.x, w=self.w,
-                                     **{"n2": 24 if self._family == "gauss" else 48, **budget}).for_dtype(dtype)
+                                     **{"n2": 24 if self._family == "gauss" else 48,
+                                        "kmax": 0 if self._family == "gauss" else 32, **budget}).for_dtype(dtype)
         self._windowedadaptation = WindowedAdaptation(warmup, windowsize=windowsize, windowscale=windowscale)
         self._scale_dir_cov = scale_dir_cov
         self._overrelaxed = overrelaxed

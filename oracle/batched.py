@@ -44,6 +44,7 @@ class FitConfig:
     n1: int = 12                     # stage-1 iteration budget
     n2: int = 24                     # stage-2 iteration budget (Newton steps)
     nb: int = 8                      # back-tracking halvings per Newton step
+    kmax: int = 0                    # cap on stage-2 KL evaluations per fit (0: 1 + n2 * nb)
     gtol1: float = 1e-8              # |l'| / sqrt(-l'') at the mode
     gtol2: float = 1e-10             # inf-norm of the scaled KL gradient
     step_cap: float = 2.0            # inf-norm cap of a stage-2 step in scaled coordinates
@@ -54,7 +55,7 @@ class FitConfig:
     @staticmethod
     def for_family(family, **kw):
         if family == "sinh":
-            base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48)
+            base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32)
         else:
             base = dict(family="gauss")
         base.update(kw)
@@ -303,13 +304,28 @@ def stage2_newton(model, theta, rho, eta0, cfg: FitConfig, x, w):
     eta = eta0.copy()
     f, g, H = kl(model, theta, rho, eta, x, w, cfg)
     nev = np.ones(B, dtype=np.int64)
+    kmax = cfg.kmax if 0 < cfg.kmax < 1 + cfg.n2 * cfg.nb else 1 + cfg.n2 * cfg.nb
     done = np.zeros(B, dtype=bool)
     conv = np.zeros(B, dtype=bool)
+    g_prev = np.full(B, np.inf)          # scaled-gradient norm when the previous direction was formed
+    basin_prev = np.zeros(B, dtype=bool)
+    slow = np.zeros(B, dtype=np.int64)
     for _ in range(cfg.n2):
         with np.errstate(all="ignore"):
             gmax = np.max(np.abs(g), axis=1)
         conv = conv | (~done & (gmax <= cfg.gtol2))
         done = done | conv
+        # flat valley of the KL surface (the 4-parameter family is nearly non-identifiable there):
+        # inside the basin Newton must at least halve the gradient; two steps in a row that do
+        # not mean the remaining descent is along a flat ridge -- stop, the fit is already
+        # tighter than the reference's own gtol (1e-3, klhr_sinh.py:199)
+        with np.errstate(all="ignore"):
+            lag = basin_prev & ~(gmax <= 0.5 * g_prev)
+        slow = np.where(done, slow, np.where(lag, slow + 1, 0))
+        done = done | (slow >= 2)
+        g_prev = np.where(done, g_prev, gmax)
+        with np.errstate(all="ignore"):
+            basin_prev = np.where(done, basin_prev, gmax <= cfg.basin)
         if done.all():
             break
         p = _newton_direction(g, H, cfg)
@@ -320,6 +336,8 @@ def stage2_newton(model, theta, rho, eta0, cfg: FitConfig, x, w):
         t = np.ones(B)
         accepted = np.zeros(B, dtype=bool)
         for _bt in range(cfg.nb):
+            out_of_budget = ~done & ~accepted & (nev >= kmax)      # evaluation cap reached: keep the iterate
+            done = done | out_of_budget
             active = ~done & ~accepted
             if not active.any():
                 break
@@ -339,6 +357,7 @@ def stage2_newton(model, theta, rho, eta0, cfg: FitConfig, x, w):
             accepted |= okk
             t = np.where(active & ~okk, t * 0.5, t)
         done = done | (~accepted)        # stalled: keep the current iterate
+        done = done | (nev >= kmax)
     with np.errstate(all="ignore"):
         conv = conv | (np.max(np.abs(g), axis=1) <= cfg.gtol2)
     return eta, nev, conv

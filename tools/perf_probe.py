@@ -21,7 +21,7 @@ dev = torch.device("cuda", 0)
 dt = torch.float64 if a.dtype == "f64" else torch.float32
 data = json.load(open(a.data[1:])) if a.data.startswith("@") else json.loads(a.data)
 model = kb.BSModel(stan_file=f"stan/{a.model}.stan", data=data, device=dev)
-base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48) if a.family == "sinh" else dict(family="gauss")
+base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32) if a.family == "sinh" else dict(family="gauss")
 fit = kb.FitConfig(**base).for_dtype(dt)
 fit.force_octet = a.octet
 D = model.dim()
