@@ -80,6 +80,30 @@ def test_against_reference_tape_directly(name):
     assert np.allclose(gpu["theta"][:-1], t["theta0"][1:], atol=1e-4)
 
 
+@pytest.mark.parametrize("N", [3, 5, 16, 32])
+@pytest.mark.parametrize("force_octet", [False, True])
+def test_other_quadrature_orders(N, force_octet):
+    """N is a constructor argument of the reference (klhr.py:20); lanes loop over nodes n, n+8, ..."""
+    import klhr_b200 as kb
+    rng = np.random.default_rng(N)
+    B = 300
+    for model, data, family in (("funnel", {"D": 3}, "gauss"), ("normal", {"D": 9}, "gauss"),
+                                ("funnel", {"D": 1}, "sinh")):
+        D = {"funnel": data["D"] + 1, "normal": data.get("D")}[model]
+        theta = rng.normal(size=(B, D)) * 0.5
+        rho = rng.normal(size=(B, D))
+        rho /= np.linalg.norm(rho, axis=1, keepdims=True)
+        xw = kb.gauss_hermite(N)
+        gpu, ref = replay_both(model, data, family, theta, rho, rng.normal(size=B), rng.normal(size=B),
+                               rng.random(B), init4=rng.normal(size=(B, 4)) if family == "sinh" else None,
+                               xw=xw, N=N, force_octet=force_octet)
+        em, es, ez, er = rel_errors(gpu, ref, family)
+        ok = ref["converged"]
+        worst = np.maximum.reduce([em, es, ez])
+        assert (worst[ok] <= 1e-10).mean() >= (0.97 if family == "sinh" else 1.0)
+        assert np.array_equal(gpu["accept"], ref["accept"])
+
+
 def test_empty_and_ragged_batches():
     import klhr_b200 as kb
     from gpu_util import up, device
