@@ -67,7 +67,8 @@ typedef struct klhr_fit {
     int32_t n1, n2, nb;          /* stage-1 iterations, stage-2 Newton steps, halvings    */
     int32_t flags;               /* KLHR_FIT_* bits                                        */
     int32_t kmax;                /* cap on stage-2 KL evaluations per fit (<= 0: 1 + n2*nb) */
-    int32_t reserved;
+    int32_t overrelax_K;         /* 0: z' = T(z) proposal (klhr.py:180); K > 0: over-relaxed proposal with
+                                    K trials (klhr.py:160-173, klhr_sinh.py:215-228), K <= 50  */
     double initscale;            /* klhr.py:24                                            */
     double tol;                  /* klhr.py:28 / klhr_sinh.py:26                          */
     double scale_clip;           /* klhr.py:30 / klhr_sinh.py:28                          */
@@ -103,6 +104,10 @@ typedef struct klhr_trace {
     void* z_prop;     /* [S][B]                                                            */
     void* u;          /* [S][B]                                                            */
     void* init4;      /* [S][B][4]    sinh family only (entries 2,3 used)                  */
+    int32_t* or_r;    /* [S][B]       over-relaxation: binomial count r (klhr.py:165)            */
+    void* or_v;       /* [S][B]       over-relaxation: beta variate v (klhr.py:168,171; 1 if unused).
+                                      Outputs of klhr_run; INPUTS of klhr_step_replay when
+                                      overrelax_K > 0                                            */
 } klhr_trace_t;
 
 /* Accumulators of a free-running launch, all optional. */

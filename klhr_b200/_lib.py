@@ -28,7 +28,7 @@ class ModelDesc(C.Structure):
 
 class FitDesc(C.Structure):
     _fields_ = [("family", C.c_int32), ("n_nodes", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
-                ("nb", C.c_int32), ("flags", C.c_int32), ("kmax", C.c_int32), ("reserved", C.c_int32),
+                ("nb", C.c_int32), ("flags", C.c_int32), ("kmax", C.c_int32), ("overrelax_K", C.c_int32),
                 ("initscale", C.c_double), ("tol", C.c_double), ("scale_clip", C.c_double),
                 ("gtol1", C.c_double), ("gtol2", C.c_double),
                 ("step_cap", C.c_double), ("c1", C.c_double), ("basin", C.c_double),
@@ -43,7 +43,8 @@ class DirectionDesc(C.Structure):
 class TraceDesc(C.Structure):
     _fields_ = [("eta", C.c_void_p), ("zp", C.c_void_p), ("r", C.c_void_p), ("accept", C.c_void_p),
                 ("evals", C.c_void_p), ("rho", C.c_void_p), ("z_init", C.c_void_p),
-                ("z_prop", C.c_void_p), ("u", C.c_void_p), ("init4", C.c_void_p)]
+                ("z_prop", C.c_void_p), ("u", C.c_void_p), ("init4", C.c_void_p), ("or_r", C.c_void_p),
+                ("or_v", C.c_void_p)]
 
 
 class AccumDesc(C.Structure):

@@ -170,6 +170,30 @@ class OnlinePCA:
         return self._solve()[0]
 
 
+class Smoother:
+    """Robbins-Monro smoother of the over-relaxation count K; same API as reference
+    ``smoother.py:3-20``.  ``update(d)`` accepts the POOLED mean of the reference's +-1 signal
+    (klhr.py:220-221: +1 whenever the chain moved, since ``_msjd`` stays 0)."""
+
+    def __init__(self, x0, kappa=-0.75):
+        self._initial = x0
+        self._x = x0
+        self._kappa = kappa
+        self._count = 0
+
+    def update(self, d):
+        self._count += 1
+        k = self._count ** self._kappa
+        self._x = k * (self._x + d) + (1 - k) * self._x
+
+    def optimum(self):
+        return self._x
+
+    def reset(self):
+        self._count = 0
+        self._x = self._initial
+
+
 def allreduce_adaptation(moments, pca, group=None, extra=()):
     """Sum the raw adaptation state over all ranks with ONE all_reduce of a flat fp64 buffer:
     [N_moments, n_pca, s1 (D), s2 (D), outer (D*D), extra...].  No-op without an initialised

@@ -65,6 +65,8 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     if (f->n1 < 0 || f->n2 < 0 || f->nb < 1) return fail(-8, "iteration budgets out of range");
     fp.family = f->family; fp.N = f->n_nodes; fp.n1 = f->n1; fp.n2 = f->n2; fp.nb = f->nb;
     fp.kmax = (f->kmax > 0 && f->kmax < 1 + f->n2 * f->nb) ? f->kmax : 1 + f->n2 * f->nb;
+    if (f->overrelax_K < 0 || f->overrelax_K > 50) return fail(-8, "overrelax_K must be in 0..50 (klhr.py:213)");
+    fp.or_K = f->overrelax_K;
     fp.initscale = f->initscale; fp.tol = f->tol; fp.scale_clip = f->scale_clip;
     fp.gtol1 = f->gtol1; fp.gtol2 = f->gtol2; fp.step_cap = f->step_cap; fp.c1 = f->c1; fp.basin = f->basin;
     for (int i = 0; i < kMaxNodes; ++i) {
@@ -228,6 +230,8 @@ int klhr_step_replay(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     a.acc.thin = 1;
     if (trace) a.tr = *trace;
     a.tr.z_init = a.tr.z_prop = a.tr.u = a.tr.init4 = nullptr;   // inputs in this mode
+    if (fit->overrelax_K > 0 && (!a.tr.or_r || !a.tr.or_v))
+        return fail(-1, "over-relaxed replay needs trace.or_r and trace.or_v as inputs");
     return cuda_fail(dispatch_step(a, dtype, fit->family, true, false, (cudaStream_t)stream, nullptr, fit->flags),
                      "klhr_step_replay");
 }

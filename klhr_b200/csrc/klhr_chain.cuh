@@ -159,7 +159,28 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
         // -------------------------------------------------------------------- fit phase (thread per chain)
         if (own_valid) {
             StepOut<R> so;
-            fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so);
+            OrCtx<R> oc;
+            oc.K = a.fp.or_K;
+            oc.inject = kReplay;
+            oc.r = 0;
+            oc.v = 1;
+            if (oc.K > 0) {
+                if constexpr (kReplay) {
+                    oc.r = a.tr.or_r[c_own];
+                    oc.v = reinterpret_cast<const R*>(a.tr.or_v)[c_own];
+                } else {
+                    const unsigned long long ocid = (unsigned long long)(a.chain_offset + c_own);
+                    const unsigned long long odraw = (unsigned long long)(a.draw_offset + step);
+                    oc.c0 = (uint32_t)ocid; oc.c1 = (uint32_t)(ocid >> 32); oc.d0 = (uint32_t)odraw;
+                    oc.k0 = (uint32_t)a.seed; oc.k1d = (uint32_t)(a.seed >> 32) ^ (uint32_t)(odraw >> 32);
+                }
+            }
+            fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so, oc);
+            if (!kReplay && oc.K > 0 && a.tr.or_r && true) {
+                a.tr.or_r[(long long)step * a.B + c_own] = oc.r;
+                reinterpret_cast<R*>(a.tr.or_v)[(long long)step * a.B + c_own] = oc.v;
+            }
+
             c_pend = so.accept ? so.zp : R(0);
             n_acc += so.accept ? 1 : 0;
             n_evals += (unsigned long long)so.evals;

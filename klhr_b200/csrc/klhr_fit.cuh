@@ -20,6 +20,7 @@ struct FitParams {
     int N;                 // quadrature nodes (<= kMaxNodes)
     int n1, n2, nb;        // stage-1 iterations, stage-2 Newton steps, halvings per step
     int kmax;              // cap on stage-2 KL evaluations
+    int or_K;              // > 0: over-relaxed proposal with K trials (klhr.py:160-173)
     double initscale, tol, scale_clip;
     double gtol1, gtol2, step_cap, c1, basin;
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
@@ -434,11 +435,61 @@ struct StepOut {
     int evals;
 };
 
+__device__ __forceinline__ double r_normcdf(double x) { return normcdf(x); }
+__device__ __forceinline__ float r_normcdf(float x) { return normcdff(x); }
+__device__ __forceinline__ double r_normcdfinv(double x) { return normcdfinv(x); }
+__device__ __forceinline__ float r_normcdfinv(float x) { return normcdfinvf(x); }
+
+// Over-relaxed proposal (Neal 1998 as used by reference klhr.py:160-173 / klhr_sinh.py:215-228):
+// u = CDF_q(0); r ~ Binomial(K, u); if r > K - r: v ~ Beta(K-r+1, 2r-K), u' = u v;
+// if r < K - r: v ~ Beta(r+1, K-2r), u' = 1 - (1-u) v; else u' = u; z' = CDF_q^{-1}(u').
+// The reference draws r and v from SciPy's global RNG; here they come from the chain's Philox
+// stream (slots 0x80000000+), or are injected in replay mode.
+template <typename R>
+struct OrCtx {
+    int K;                       // 0: standard proposal
+    bool inject;                 // replay: r and v are inputs
+    int r;
+    R v;
+    uint32_t c0, c1, d0, k0, k1d;
+};
+
+template <typename R>
+__device__ inline void overrelax_sample(OrCtx<R>& oc, R u0) {
+    const int K = oc.K;
+    uint32_t w[4];
+    int have = 0, q = 0;
+    auto next_u = [&]() -> float {
+        if (have == 0) {
+            Philox::block(oc.c0, oc.c1, oc.d0, 0x80000000u + (uint32_t)q, oc.k0, oc.k1d, w);
+            ++q;
+            have = 4;
+        }
+        const float x = u01_32(w[4 - have]);
+        --have;
+        return x;
+    };
+    int r = 0;
+    for (int k = 0; k < K; ++k) r += ((R)next_u() < u0) ? 1 : 0;
+    int na = 0, nb = 0;
+    if (r > K - r) { na = K - r + 1; nb = 2 * r - K; }
+    else if (r < K - r) { na = r + 1; nb = K - 2 * r; }
+    R v = 1;
+    if (na > 0) {                // Beta(a, b), integer a, b: Ga / (Ga + Gb) with Gamma(n) = -sum log U
+        float ga = 0, gb = 0;
+        for (int i = 0; i < na; ++i) ga -= __logf(next_u());
+        for (int i = 0; i < nb; ++i) gb -= __logf(next_u());
+        v = (R)(ga / (ga + gb));
+    }
+    oc.r = r;
+    oc.v = v;
+}
+
 // z_init, init2/init3 (sinh start for log d, e), z_prop, u are the step's variates
 // (reference draw order: klhr.py:129,180,188 ; klhr_sinh.py:184,191,246,255).
 template <int G, typename R, typename Model, int n>
 __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams& fp, int lane, unsigned m,
-                                R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o) {
+                                R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o, OrCtx<R>& oc) {
     R xi, tau0;
     int nev1, nev2;
     stage1_mode<G, R, Model>(cf, z_init, fp, lane, m, xi, tau0, nev1);
@@ -455,6 +506,14 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
     if constexpr (n == 2) {
         const R c = (R)fp.scale_clip;
         const R s = r_exp(r_clamp(eta[1], -c, c));
+        if (oc.K > 0) {                             // klhr.py:160-173
+            const R u0 = r_normcdf((R(0) - eta[0]) / s);
+            if (!oc.inject) overrelax_sample<R>(oc, u0);
+            R up = u0;
+            if (oc.r > oc.K - oc.r) up = u0 * oc.v;
+            else if (oc.r < oc.K - oc.r) up = R(1) - (R(1) - u0) * oc.v;
+            z_prop = r_normcdfinv(up);
+        }
         zp = eta[0] + s * z_prop;                   // klhr.py:180
         // _logq(0) - _logq(zp) (klhr.py:155-158,185-186): the two -log(s) terms cancel, so only
         // the quadratic parts are formed (saves two logs and two exps per draw)
@@ -462,6 +521,17 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
         lq0 = -R(0.5) * z0 * z0;
         lq1 = -R(0.5) * z1 * z1;
     } else {
+        if (oc.K > 0) {                             // klhr_sinh.py:215-228
+            const SinhPar<R> q = sinh_unpack<R>(eta, fp);
+            const R c = (R)fp.scale_clip;
+            const R z0 = (R(0) - q.m) / q.s;
+            const R u0 = r_normcdf(r_sinh(r_clamp(q.d * r_asinh(z0) - q.e, -c, c)));    // _CDF(0), :131-133
+            if (!oc.inject) overrelax_sample<R>(oc, u0);
+            R up = u0;
+            if (oc.r > oc.K - oc.r) up = u0 * oc.v;
+            else if (oc.r < oc.K - oc.r) up = R(1) - (R(1) - u0) * oc.v;
+            z_prop = r_normcdfinv(up);              // _CDF_inv, :135-137
+        }
         zp = transport_sinh<R>(z_prop, eta, fp);    // klhr_sinh.py:246
         lq0 = logq_sinh<R>(R(0), eta, fp);
         lq1 = logq_sinh<R>(zp, eta, fp);

@@ -237,7 +237,28 @@ __global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const 
             if (!valid) continue;
             // ---------------------------------------------------------------- 3.+4. fit, propose, MH
             StepOut<R> so;
-            fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so);
+            OrCtx<R> oc;
+            oc.K = a.fp.or_K;
+            oc.inject = kReplay;
+            oc.r = 0;
+            oc.v = 1;
+            if (oc.K > 0) {
+                if constexpr (kReplay) {
+                    oc.r = a.tr.or_r[c];
+                    oc.v = reinterpret_cast<const R*>(a.tr.or_v)[c];
+                } else {
+                    const unsigned long long ocid = (unsigned long long)(a.chain_offset + c);
+                    const unsigned long long odraw = (unsigned long long)(a.draw_offset + step);
+                    oc.c0 = (uint32_t)ocid; oc.c1 = (uint32_t)(ocid >> 32); oc.d0 = (uint32_t)odraw;
+                    oc.k0 = (uint32_t)a.seed; oc.k1d = (uint32_t)(a.seed >> 32) ^ (uint32_t)(odraw >> 32);
+                }
+            }
+            fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so, oc);
+            if (!kReplay && oc.K > 0 && a.tr.or_r && lane == 0) {
+                a.tr.or_r[row] = oc.r;
+                reinterpret_cast<R*>(a.tr.or_v)[row] = oc.v;
+            }
+
             if (so.accept) {
                 for (int i = lane; i < D; i += kOct) th[i] = th[i] + so.zp * rh[i];
                 ++n_acc;

@@ -40,6 +40,7 @@ class FitConfig:
     n2: int = 24
     nb: int = 8
     kmax: int = 0                      # cap on stage-2 KL evaluations (0: 1 + n2 * nb)
+    overrelax_K: int = 0               # K > 0: over-relaxed proposals with K trials (klhr.py:160-173)
     gtol1: float = 1e-8
     gtol2: float = 1e-10
     step_cap: float = 2.0
@@ -69,7 +70,8 @@ class FitConfig:
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin, flags=1 if self.force_octet else 0, kmax=int(self.kmax))
+                         basin=self.basin, flags=1 if self.force_octet else 0, kmax=int(self.kmax),
+                         overrelax_K=int(self.overrelax_K))
         for i in range(self.N):
             d.x[i] = float(self.x[i])
             d.w[i] = float(self.w[i])
@@ -104,16 +106,22 @@ class Trace:
         self.z_prop = z(S, B) if variates else None
         self.u = z(S, B) if variates else None
         self.init4 = z(S, B, 4) if variates and n_eta == 4 else None
+        self.or_r = z(S, B, dt=torch.int32) if variates else None
+        self.or_v = z(S, B) if variates else None
 
     def descriptor(self):
         return _lib.TraceDesc(eta=_ptr(self.eta), zp=_ptr(self.zp), r=_ptr(self.r), accept=_ptr(self.accept),
                               evals=_ptr(self.evals), rho=_ptr(self.rho), z_init=_ptr(self.z_init),
-                              z_prop=_ptr(self.z_prop), u=_ptr(self.u), init4=_ptr(self.init4))
+                              z_prop=_ptr(self.z_prop), u=_ptr(self.u), init4=_ptr(self.init4),
+                              or_r=_ptr(self.or_r), or_v=_ptr(self.or_v))
 
 
-def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, init4=None, trace=True):
+def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, init4=None, trace=True,
+                or_r=None, or_v=None):
     """One draw for every chain with host-injected direction and variates; ``theta`` (B, D)
-    is advanced IN PLACE.  Returns a ``Trace`` (S = 1) or None."""
+    is advanced IN PLACE.  Returns a ``Trace`` (S = 1) or None.  With ``fit.overrelax_K > 0`` the
+    binomial counts ``or_r`` (int32) and beta variates ``or_v`` of the over-relaxed proposal are
+    injected too."""
     lib = _lib.load()
     for t, n in ((theta, "theta"), (rho, "rho"), (z_init, "z_init"), (z_prop, "z_prop"), (u, "u")):
         _require_cuda(t, n)
@@ -125,8 +133,16 @@ def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, i
         if init4 is None:
             raise ValueError("sinh family needs init4")
         _require_cuda(init4, "init4")
+    if fit.overrelax_K > 0:
+        if or_r is None or or_v is None:
+            raise ValueError("over-relaxed replay needs or_r and or_v")
+        _require_cuda(or_r, "or_r")
+        _require_cuda(or_v, "or_v")
+        trace = True
     tr = Trace(1, B, D, fit.n_eta, dtype, dev, rho=False) if trace else None
     trd = tr.descriptor() if tr else None
+    if fit.overrelax_K > 0:
+        trd.or_r, trd.or_v = or_r.data_ptr(), or_v.data_ptr()
     md, fd = model.descriptor(dtype, dev), fit.descriptor()
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream(dev).cuda_stream

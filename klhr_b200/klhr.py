@@ -17,7 +17,8 @@ Documented deviations from the reference (DESIGN.md has the full list)
   * ``theta=`` is honoured (the reference's ``_initialize`` overwrites it, klhr.py:94);
   * adaptation pools over chains instead of over one chain's history; the PCA is the
     eigen-decomposition of the pooled second-moment matrix, sampled every ``pca_stride`` draws;
-  * ``overrelaxed=True`` is not implemented and raises.
+  * over-relaxed proposals (klhr.py:160-173) draw their binomial / beta variates from the chain's
+    Philox stream instead of SciPy's global RNG; the Smoother signal that adapts K is pooled.
 """
 from __future__ import annotations
 
@@ -25,13 +26,14 @@ import numpy as np
 import torch
 
 from . import engine
-from .adaptation import OnlineMoments, OnlinePCA, WindowedAdaptation, allreduce_adaptation
+from .adaptation import OnlineMoments, OnlinePCA, Smoother, WindowedAdaptation, allreduce_adaptation
 from .mcmc import MCMCBase
 
 
 class KLHR(MCMCBase):
     _family = "gauss"
     _eigen_weights_normalised = False          # klhr.py:150 sums evals * eigvecs (un-normalised)
+    _adapt_K = True                            # klhr.py:212-214 adapts K at window closures
 
     def __init__(self, bsmodel, theta=None, seed=None, N=8, K=10, J=2, l=4, initscale=0.1, warmup=1_000,
                  windowsize=50, windowscale=2, tol=1e-12, grad_clip=1e15, scale_clip=600,
@@ -39,10 +41,9 @@ class KLHR(MCMCBase):
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
                  pca_stride=10, fit_budget=None):
         super().__init__(bsmodel, -1, theta=theta, seed=seed, chains=chains, dtype=dtype, device=device)
-        if overrelaxed:
-            raise NotImplementedError("over-relaxed proposals are not implemented on the device path "
-                                      "(SURVEY.md section 8f N2); pass overrelaxed=False")
-        self.N, self.K, self.l = N, K, l
+        if not 1 <= int(K) <= 50:
+            raise ValueError("K must be in 1..50 (the reference clips it there, klhr.py:213)")
+        self.N, self.K, self.l = N, int(K), l
         self.J = self._clip_J(J)
         self._tol, self._grad_clip, self._scale_clip = tol, grad_clip, scale_clip
         self._max_init_tries = max_init_tries
@@ -53,6 +54,8 @@ class KLHR(MCMCBase):
                                      scale_clip=float(scale_clip), x=self.x, w=self.w,
                                      **{"n2": 24 if self._family == "gauss" else 48,
                                         "kmax": 0 if self._family == "gauss" else 32, **budget}).for_dtype(dtype)
+        self._fit.overrelax_K = self.K if overrelaxed else 0       # klhr.py:160-173 / klhr_sinh.py:215-228
+        self._smoothK = Smoother(self.K)
         self._windowedadaptation = WindowedAdaptation(warmup, windowsize=windowsize, windowscale=windowscale)
         self._scale_dir_cov = scale_dir_cov
         self._overrelaxed = overrelaxed
@@ -69,6 +72,7 @@ class KLHR(MCMCBase):
         self._eigvecs = np.zeros((self.D, ncol))
         self._eigvals = np.ones(ncol)
         self._draw = 0
+        self._acc_seen = 0.0
         self._accept_count = torch.zeros(self.chains, dtype=torch.int64, device=dev)
         self._evals_total = torch.zeros(1, dtype=torch.int64, device=dev)
         if chain_offset is None:
@@ -149,6 +153,13 @@ class KLHR(MCMCBase):
                        chain_offset=self._chain_offset, draw_offset=self._draw,
                        accept_count=self._accept_count, evals_total=self._evals_total,
                        draws=draws, thin=thin, thin_offset=done, **kw)
+            if adapting and self._overrelaxed and self._adapt_K:
+                # pooled Smoother signal (klhr.py:219-221): +1 for a chain that moved, -1 otherwise
+                acc_now = float(self._accept_count.double().mean())
+                frac = (acc_now - self._acc_seen) / steps
+                self._acc_seen = acc_now
+                for _ in range(steps - (1 if closes else 0)):
+                    self._smoothK.update(2.0 * frac - 1.0)
             self._draw += steps
             done += steps
             if adapting:
@@ -183,6 +194,10 @@ class KLHR(MCMCBase):
         mom.reset(shift=mean64)
         gmom.reset()
         pca.reset()
+        if self._overrelaxed and self._adapt_K:                    # klhr.py:212-214
+            self.K = int(np.clip(self._smoothK.optimum(), 1, 50))
+            self._fit.overrelax_K = self.K
+        self._smoothK.reset()
         self._refresh_direction()
 
     # ------------------------------------------------------------------ public API

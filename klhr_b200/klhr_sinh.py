@@ -2,10 +2,9 @@
 
 Drop-in for reference ``klhr_sinh.py:14-289``: constructor keywords and defaults of
 klhr_sinh.py:15-32 (``tol=1e-10``, ``scale_clip=300``, ``eigen_method_one=False``), no
-clipping of ``J`` (:37) and normalised eigenvalue weights in the method-two direction mean
-(:210).  ``overrelaxed`` defaults to True in the reference (:30); the over-relaxed proposal
-draws from SciPy's global RNG and is not on the device path, so
-the default here is False and True raises.
+clipping of ``J`` (:37), normalised eigenvalue weights in the method-two direction mean
+(:210), ``overrelaxed=True`` (:30) with the over-relaxed proposal of :215-228 (binomial / beta
+variates from the chain's Philox stream instead of SciPy's global RNG) and a fixed K (:279).
 """
 from __future__ import annotations
 
@@ -17,10 +16,11 @@ from .klhr import KLHR
 class KLHRSINH(KLHR):
     _family = "sinh"
     _eigen_weights_normalised = True           # klhr_sinh.py:210 uses p = evals / sum(evals)
+    _adapt_K = False                           # klhr_sinh.py:279 has the K update commented out
 
     def __init__(self, bsmodel, theta=None, seed=None, N=8, K=10, J=2, l=4, initscale=0.1, warmup=1_000,
                  windowsize=50, windowscale=2, tol=1e-10, grad_clip=1e15, scale_clip=300,
-                 scale_dir_cov=False, overrelaxed=False, eigen_method_one=False, max_init_tries=100, *,
+                 scale_dir_cov=False, overrelaxed=True, eigen_method_one=False, max_init_tries=100, *,
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
                  pca_stride=10, fit_budget=None):
         if dtype != torch.float64:

@@ -413,19 +413,41 @@ def fit(model, theta, rho, z_init, cfg: FitConfig, init4=None, xw=None):
     return eta, nev1 + nev2 * cfg.N, conv
 
 
-def step(model, theta, rho, z_init, z_prop, u, cfg: FitConfig, init4=None, xw=None):
+def overrelaxed_quantile(u0, K, r, v):
+    """u' of the over-relaxed proposal given u = CDF_q(0), the binomial count r and the beta
+    variate v (reference ``klhr.py:163-172`` / ``klhr_sinh.py:217-227``)."""
+    up = np.array(u0, dtype=np.float64, copy=True)
+    hi = r > K - r
+    lo = r < K - r
+    up = np.where(hi, u0 * v, up)
+    up = np.where(lo, 1.0 - (1.0 - u0) * v, up)
+    return up
+
+
+def step(model, theta, rho, z_init, z_prop, u, cfg: FitConfig, init4=None, xw=None, or_K=0, or_r=None,
+         or_v=None):
     """One KLHR draw for every chain.  Returns a dict with eta, zp, r, accept, theta
-    (after the step), evals (line evaluations executed), converged."""
+    (after the step), evals (line evaluations executed), converged.  ``or_K > 0``: over-relaxed
+    proposal with injected binomial counts ``or_r`` and beta variates ``or_v``."""
+    import scipy.special as sp
     theta = np.asarray(theta, dtype=np.float64)
     rho = np.asarray(rho, dtype=np.float64)
     eta, evals, conv = fit(model, theta, rho, z_init, cfg, init4=init4, xw=xw)
     if cfg.family == "gauss":
         with np.errstate(all="ignore"):
             s = np.exp(np.clip(eta[:, 1], -cfg.scale_clip, cfg.scale_clip))
+            if or_K > 0:                                         # klhr.py:160-173
+                u0 = sp.ndtr((0.0 - eta[:, 0]) / s)
+                z_prop = sp.ndtri(overrelaxed_quantile(u0, or_K, or_r, or_v))
             zp = eta[:, 0] + s * z_prop
         lq0 = logq_gauss(np.zeros_like(zp), eta, cfg)
         lq1 = logq_gauss(zp, eta, cfg)
     else:
+        if or_K > 0:                                             # klhr_sinh.py:215-228
+            m_, s_, d_, e_ = _sinh_unpack(eta, cfg)
+            with np.errstate(all="ignore"):
+                ti0 = np.sinh(np.clip(d_ * np.arcsinh((0.0 - m_) / s_) - e_, -cfg.scale_clip, cfg.scale_clip))
+                z_prop = sp.ndtri(overrelaxed_quantile(sp.ndtr(ti0), or_K, or_r, or_v))
         zp = transport_sinh(z_prop, eta, cfg)
         lq0 = logq_sinh(np.zeros_like(zp), eta, cfg)
         lq1 = logq_sinh(zp, eta, cfg)

@@ -176,6 +176,21 @@ CASES = [
     ("stats_funnel_d2_sinh_noadapt", "funnel", {"D": 1}, "sinh", 6_000,
      dict(seed=92, warmup=0, overrelaxed=False), None),
     ("stats_rosenbrock_d4_klhr_noadapt", "rosenbrock", {"D": 2}, "gauss", 20_000, dict(seed=93, warmup=0), None),
+    # over-relaxed proposals (klhr.py:160-173; default ON in KLHRSINH, klhr_sinh.py:30): r and v come from
+    # SciPy's global RNG, seeded here with np.random.seed(case seed) so the runs are reproducible
+    ("stats_funnel_d2_klhr_overrelaxed", "funnel", {"D": 1}, "gauss", 20_000,
+     dict(seed=94, warmup=0, overrelaxed=True), None),
+    ("stats_funnel_d2_sinh_overrelaxed", "funnel", {"D": 1}, "sinh", 5_000,
+     dict(seed=95, warmup=0, overrelaxed=True), None),
+]
+
+# seeded free runs of the unmodified reference WITHOUT the tape RNG (its own PCG64 stream, its own
+# multivariate_normal): the port must reproduce the whole trajectory bit for bit from the seed
+FREERUNS = [
+    ("freerun_funnel_d2_klhr_adapt", "funnel", {"D": 1}, "gauss", 160, dict(seed=3, warmup=100)),
+    ("freerun_funnel_d2_klhr_overrelaxed", "funnel", {"D": 1}, "gauss", 150, dict(seed=4, warmup=0, overrelaxed=True)),
+    ("freerun_funnel_d2_sinh_overrelaxed", "funnel", {"D": 1}, "sinh", 120, dict(seed=5, warmup=0, overrelaxed=True)),
+    ("freerun_illnormal_d20_klhr_adapt", "ill-normal", {"D": 20}, "gauss", 130, dict(seed=6, warmup=100)),
 ]
 
 
@@ -198,6 +213,23 @@ def main():
 
     out_dir = Path(args.out)
     out_dir.mkdir(parents=True, exist_ok=True)
+
+    for name, stem, data, family, M, kw in FREERUNS:
+        if args.only and args.only not in name:
+            continue
+        model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
+        cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
+        (ref_klhr if family == "gauss" else ref_sinh).minimize = scipy.optimize.minimize
+        algo = cls(model, **kw)
+        np.random.seed(kw["seed"])                      # SciPy's global RNG (over-relaxed proposals)
+        thetas = np.array([algo.draw() for _ in range(M)])
+        meta = dict(case=name, model=stem, family=family, draws=M, ctor=kw, numpy=np.__version__,
+                    scipy=scipy.__version__)
+        np.savez_compressed(out_dir / f"{name}.npz", thetas=thetas,
+                            acceptance_probability=np.array(float(np.ravel(algo.acceptance_probability)[0])),
+                            grad_evals=np.array(int(algo.grad_evals)), meta_json=np.array(json.dumps(meta)),
+                            data_json=np.array(json.dumps(data)))
+        print(f"{name:36s} draws={M:6d} acc={float(np.ravel(algo.acceptance_probability)[0]):.3f}")
 
     for name, stem, data, family, M, kw, gtol in CASES:
         if args.only and args.only not in name:
@@ -222,8 +254,24 @@ def main():
         kw = dict(kw)
         # construct with a plain seed (the ctor draws the start point), then tape
         algo = cls(model, seed=seed, **kw)
-        algo.rng = TapeRNG(seed + 1000)
-        tape = _tape_run(algo, M, family)
+        np.random.seed(seed)                            # SciPy's global RNG (over-relaxed proposals)
+        if name.startswith("stats_") and kw.get("overrelaxed"):
+            # plain seeded run (no tape RNG: the over-relaxed step consumes no proposal normal)
+            acc, th = [], []
+            for _ in range(M):
+                th.append(np.array(algo.theta, copy=True))
+                prev = float(np.ravel(algo.acceptance_probability)[0])
+                algo.draw()
+                new = float(np.ravel(algo.acceptance_probability)[0])
+                # the MH flag itself (klhr.py:188-193): an over-relaxed proposal can land exactly on the
+                # current point (r == K - r), which is an ACCEPTED move that leaves theta unchanged
+                acc.append(bool(round(prev + (new - prev) * algo._draw)))
+            tape = {"accept": np.array(acc), "theta0": np.array(th), "theta_last": np.array(algo.theta),
+                    "acceptance_probability": np.array(float(np.ravel(algo.acceptance_probability)[0])),
+                    "grad_evals": np.array(int(algo.grad_evals))}
+        else:
+            algo.rng = TapeRNG(seed + 1000)
+            tape = _tape_run(algo, M, family)
         if name.startswith("stats_"):
             tape = {"accept": tape["accept"], "theta_thin10": tape["theta0"][::10],
                     "acceptance_probability": tape["acceptance_probability"],

@@ -168,17 +168,18 @@ class ChainSampler:
     """One chain of KLHR (family="gauss") or KLHRSINH (family="sinh").
 
     Keyword names and defaults are the reference's (``klhr.py:16-34``,
-    ``klhr_sinh.py:15-32``).  Over-relaxed proposals are not ported (SURVEY.md section 8f
-    N2: they draw from SciPy's global RNG and cannot be replayed).
+    ``klhr_sinh.py:15-32``) except ``overrelaxed`` (False for both families here).  Over-relaxed
+    proposals draw r and v from SciPy's global RNG like the reference; the Smoother-adapted K
+    (``klhr.py:212-214``) is not ported: K stays at its constructor value.
     """
 
     def __init__(self, model, family="gauss", theta=None, seed=None, rng=None, N=8, K=10, J=2,
                  l=4, initscale=0.1, warmup=1_000, windowsize=50, windowscale=2, tol=None,
                  grad_clip=1e15, scale_clip=None, scale_dir_cov=False, overrelaxed=False,
                  eigen_method_one=None, max_init_tries=100):
-        if overrelaxed:
-            raise NotImplementedError("over-relaxed proposals are outside the ported path")
         gauss = family == "gauss"
+        self.overrelaxed = overrelaxed
+        self.K = K
         tol = (1e-12 if gauss else 1e-10) if tol is None else tol
         scale_clip = (600 if gauss else 300) if scale_clip is None else scale_clip
         eigen_method_one = gauss if eigen_method_one is None else eigen_method_one
@@ -207,8 +208,9 @@ class ChainSampler:
         self.grad_evals = 0
         if theta is not None:
             self.theta = np.array(theta, dtype=np.float64)
-        else:                                                            # klhr.py:87-99
-            for _ in range(max_init_tries):
+        else:
+            self.rng.normal(scale=0.1, size=self.D)                      # mcmc.py:14-17 (then overwritten)
+            for _ in range(max_init_tries):                              # klhr.py:87-99
                 cand = self.rng.normal(size=self.D) * initscale
                 lp, g = model.log_density_gradient(cand)
                 if np.isfinite(lp) and np.isfinite(np.linalg.norm(g)):
@@ -252,9 +254,38 @@ class ChainSampler:
         return o2.x
 
     # ------------------------------------------------------------------------- MH (H8)
+    def overrelaxed_proposal(self, eta):
+        """reference ``klhr.py:160-173`` / ``klhr_sinh.py:215-228``; r and v come from SciPy's
+        GLOBAL RandomState exactly like the reference (seed it with ``np.random.seed``)."""
+        import scipy.stats as st
+        K = self.K
+        if self.family_name == "gauss":
+            m, s = self.line.unpack(eta)
+            dist = st.norm(m, s)
+            u = dist.cdf(np.array([0]))
+            up = u
+        else:
+            u = sp.ndtr(self.line.transport_inv(np.zeros(1), eta))
+            up = 0
+        r = st.binom(K, u).rvs()
+        if r > K - r:
+            v = st.beta(K - r + 1, 2 * r - K).rvs()
+            up = u * v
+        elif r < K - r:
+            v = st.beta(r + 1, K - 2 * r).rvs()
+            up = 1 - (1 - u) * v
+        elif self.family_name != "gauss":
+            up = u
+        if self.family_name == "gauss":
+            return dist.ppf(up)
+        return self.line.transport(sp.ndtri(up), eta)
+
     def metropolis(self, eta, rho):
-        z = self.rng.normal(size=1)
-        zp = self.line.propose(eta, z)
+        if self.overrelaxed:
+            zp = self.overrelaxed_proposal(eta)
+        else:
+            z = self.rng.normal(size=1)
+            zp = self.line.propose(eta, z)
         cand = zp * rho + self.theta
         r = self.model.log_density(cand)
         r -= self.model.log_density(self.theta)

@@ -31,6 +31,26 @@ def test_port_is_bit_exact_on_reference_tape(tapes, name, n):
         assert np.array_equal(s.eigvals, t["closure_eigvals"][k - 1])
 
 
+@pytest.mark.parametrize("name", ["freerun_funnel_d2_klhr_adapt", "freerun_funnel_d2_klhr_overrelaxed",
+                                  "freerun_funnel_d2_sinh_overrelaxed", "freerun_illnormal_d20_klhr_adapt"])
+def test_port_reproduces_seeded_free_runs_of_the_reference(name):
+    """No tape RNG here: the unmodified reference ran from a seed with its own PCG64 stream,
+    multivariate_normal, window adaptation and (where enabled) over-relaxed proposals drawing from
+    SciPy's global RNG; the port reproduces the whole trajectory bit for bit."""
+    import json
+    from conftest import GOLDEN
+    from oracle.ref_port import ChainSampler
+    t = dict(np.load(GOLDEN / f"{name}.npz"))
+    meta, data = json.loads(str(t["meta_json"])), json.loads(str(t["data_json"]))
+    model = BSModel(stan_file=meta["model"] + ".stan", data=data)
+    s = ChainSampler(model, family=meta["family"], **meta["ctor"])
+    np.random.seed(meta["ctor"]["seed"])
+    out = np.array([s.draw() for _ in range(meta["draws"])])
+    assert np.array_equal(out, t["thetas"])
+    assert float(np.ravel(s.acceptance_probability)[0]) == float(t["acceptance_probability"])
+    assert s.grad_evals == int(t["grad_evals"])
+
+
 def test_quadrature_table(tapes):
     # SURVEY.md 8c (3): values after the reference's normalisation, klhr.py:46-49
     from oracle.ref_port import gauss_hermite_probabilists
