@@ -39,7 +39,8 @@ enum {
     KLHR_MODEL_AR1 = 4,         /* stan/ar1.stan          s0 = alpha, s1 = 1/beta^2               */
     KLHR_MODEL_ARK = 5,         /* stan/arK.stan          i0 = K, i1 = T-K, data0 = [G|c|yy]      */
     KLHR_MODEL_ROSENBROCK = 6,  /* stan/rosenbrock.stan   i0 = D; dim = 2 D                       */
-    KLHR_MODEL_COUNT = 7
+    KLHR_MODEL_EARNINGS = 7,    /* stan/earnings.stan     data0 = [N, Se, Sh, See, Seh, Shh]; dim = 4 */
+    KLHR_MODEL_COUNT = 8
 };
 
 /* Target density descriptor (replaces a bridgestan.StanModel handle, bsmodel.py:10-13). */

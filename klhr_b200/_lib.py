@@ -18,7 +18,7 @@ FAMILY_GAUSS, FAMILY_SINH = 0, 1
 MAX_NODES = 32
 
 MODEL_IDS = {"normal": 0, "ill-normal": 1, "funnel": 2, "corr-normal": 3, "ar1": 4, "arK": 5,
-             "rosenbrock": 6}
+             "rosenbrock": 6, "earnings": 7}
 
 
 class ModelDesc(C.Structure):

@@ -88,6 +88,12 @@ class BSModel:
             h.update(dim=K + 2, i0=K, i1=nobs, data0=pack)
         elif n == "rosenbrock":                      # stan/rosenbrock.stan:4-7
             h.update(dim=2 * int(d["D"]), i0=int(d["D"]))
+        elif n == "earnings":                        # stan/earnings.stan:1-17, sufficient statistics
+            e = np.asarray(d["earn"], dtype=np.float64)
+            ht = np.asarray(d["height"], dtype=np.float64)
+            if e.shape != (int(d["N"]),) or ht.shape != e.shape:
+                raise ValueError("earnings: earn and height must have length N")
+            h.update(dim=4, data0=np.array([float(len(e)), e.sum(), ht.sum(), e @ e, e @ ht, ht @ ht]))
         return h
 
     def dim(self):
@@ -154,12 +160,16 @@ class BSModel:
         out = theta.clone() if torch.is_tensor(theta) else np.array(theta, dtype=np.float64)
         if self.name == "arK":                       # sigma = exp(u), stan/arK.stan:9
             out[..., -1] = torch.exp(out[..., -1]) if torch.is_tensor(out) else np.exp(out[..., -1])
+        if self.name == "earnings":                  # sigma, s > 0, stan/earnings.stan:9-10
+            out[..., 2:] = torch.exp(out[..., 2:]) if torch.is_tensor(out) else np.exp(out[..., 2:])
         return out
 
     def unconstrain(self, theta):
         out = theta.clone() if torch.is_tensor(theta) else np.array(theta, dtype=np.float64)
         if self.name == "arK":
             out[..., -1] = torch.log(out[..., -1]) if torch.is_tensor(out) else np.log(out[..., -1])
+        if self.name == "earnings":
+            out[..., 2:] = torch.log(out[..., 2:]) if torch.is_tensor(out) else np.log(out[..., 2:])
         return out
 
     def parameter_names(self):
@@ -168,6 +178,8 @@ class BSModel:
             return ["double_log_sigma"] + [f"alpha.{i + 1}" for i in range(h["i0"])]
         if self.name == "arK":
             return ["alpha"] + [f"beta.{i + 1}" for i in range(h["i0"])] + ["sigma"]
+        if self.name == "earnings":
+            return ["beta.1", "beta.2", "sigma", "s"]
         if self.name == "rosenbrock":
             return [f"v.{i + 1}" for i in range(h["i0"])] + [f"theta.{i + 1}" for i in range(h["i0"])]
         return [f"y.{i + 1}" for i in range(h["dim"])]

@@ -53,6 +53,9 @@ static int check_model(const klhr_model_t* m, ModelParams& mp) {
         case KLHR_MODEL_AR1:
             if (!(m->s1 > 0)) return fail(-5, "ar1: s1 = 1/beta^2 must be positive");
             break;
+        case KLHR_MODEL_EARNINGS:
+            if (!m->data0 || m->dim != 4) return fail(-5, "earnings: need data0 = [N,Se,Sh,See,Seh,Shh], dim = 4");
+            break;
         default: break;
     }
     return 0;
@@ -103,6 +106,7 @@ static int dispatch_chain(const StepArgs& a, int dtype, int family, bool replay,
         case KLHR_MODEL_AR1: return launch_chain_ar1(a, dtype, family, replay, st, info);
         case KLHR_MODEL_ARK: return launch_chain_ark(a, dtype, family, replay, st, info);
         case KLHR_MODEL_ROSENBROCK: return launch_chain_rosenbrock(a, dtype, family, replay, st, info);
+        case KLHR_MODEL_EARNINGS: return launch_chain_earnings(a, dtype, family, replay, st, info);
     }
     return fail(-2, "unknown model id");
 }
@@ -119,6 +123,7 @@ static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, 
         case KLHR_MODEL_AR1: return launch_step_ar1(a, dtype, family, replay, accum, st, info);
         case KLHR_MODEL_ARK: return launch_step_ark(a, dtype, family, replay, accum, st, info);
         case KLHR_MODEL_ROSENBROCK: return launch_step_rosenbrock(a, dtype, family, replay, accum, st, info);
+        case KLHR_MODEL_EARNINGS: return launch_step_earnings(a, dtype, family, replay, accum, st, info);
     }
     return fail(-2, "unknown model id");
 }
@@ -207,6 +212,7 @@ int klhr_model_eval(const klhr_model_t* model, int dtype, const void* theta_dev,
         case KLHR_MODEL_AR1: e = launch_eval_ar1(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
         case KLHR_MODEL_ARK: e = launch_eval_ark(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
         case KLHR_MODEL_ROSENBROCK: e = launch_eval_rosenbrock(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
+        case KLHR_MODEL_EARNINGS: e = launch_eval_earnings(mp, dtype, theta_dev, lp_dev, grad_dev, n_chains, st); break;
     }
     return cuda_fail(e, "klhr_model_eval");
 }

@@ -274,5 +274,6 @@ KLHR_DECLARE_MODEL_CHAIN(corr_normal)
 KLHR_DECLARE_MODEL_CHAIN(ar1)
 KLHR_DECLARE_MODEL_CHAIN(ark)
 KLHR_DECLARE_MODEL_CHAIN(rosenbrock)
+KLHR_DECLARE_MODEL_CHAIN(earnings)
 
 }  // namespace klhr

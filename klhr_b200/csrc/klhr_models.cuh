@@ -331,4 +331,89 @@ struct ARK {
     }
 };
 
+// ---- stan/earnings.stan:1-17   unconstrained [b1, b2, us = log sigma, ut = log s]
+// (the model of the reference's self-tests, klhr.py:238, and relaxation experiment).
+// Sufficient statistics (host, fp64) packed as [N, Se, Sh, See, Seh, Shh] with e = earn, h = height:
+// SSR(b) = See - 2 b1 Se - 2 b2 Seh + b1^2 N + 2 b1 b2 Sh + b2^2 Shh.
+template <typename R>
+struct Earnings {
+    static constexpr bool kDenseCta = false;
+    struct Coef { R b1, b2, r1, r2, us0, rs, ut0, rt, S0, S1, S2, nm1, l0; };
+    struct Stats { R N, Se, Sh, See, Seh, Shh; };
+    __device__ static __forceinline__ Stats stats(const ModelParams& mp) {
+        const R* p = reinterpret_cast<const R*>(mp.p0);
+        Stats s;
+        s.N = __ldg(p); s.Se = __ldg(p + 1); s.Sh = __ldg(p + 2);
+        s.See = __ldg(p + 3); s.Seh = __ldg(p + 4); s.Shh = __ldg(p + 5);
+        return s;
+    }
+    __device__ static __forceinline__ R student(R w) { return -R(3) * r_log1p(w * w / R(5)); }
+    __device__ static __forceinline__ R value(const Coef& c, R y) {
+        const R us = c.us0 + y * c.rs, ut = c.ut0 + y * c.rt;
+        const R emt = r_exp(-ut);
+        const R w1 = (c.b1 + y * c.r1) * emt, w2 = (c.b2 + y * c.r2) * emt;
+        const R S = c.S0 + y * (R(2) * c.S1 + y * c.S2);
+        return -R(0.01) * r_exp(ut) - ut + student(w1) + student(w2) - R(0.1) * r_exp(us) - c.nm1 * us
+               - R(0.5) * r_exp(-R(2) * us) * S;
+    }
+    // D = 4: every lane computes the same coefficients, no reductions needed
+    __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
+        const Stats s = stats(mp);
+        Coef c;
+        c.b1 = th[0]; c.b2 = th[1]; c.us0 = th[2]; c.ut0 = th[3];
+        c.r1 = rh[0]; c.r2 = rh[1]; c.rs = rh[2]; c.rt = rh[3];
+        c.S0 = s.See - R(2) * c.b1 * s.Se - R(2) * c.b2 * s.Seh + c.b1 * c.b1 * s.N + R(2) * c.b1 * c.b2 * s.Sh
+               + c.b2 * c.b2 * s.Shh;
+        // X^T r with r = e - b1 - b2 h
+        const R xr1 = s.Se - c.b1 * s.N - c.b2 * s.Sh;
+        const R xr2 = s.Seh - c.b1 * s.Sh - c.b2 * s.Shh;
+        c.S1 = -(c.r1 * xr1 + c.r2 * xr2);
+        c.S2 = c.r1 * c.r1 * s.N + R(2) * c.r1 * c.r2 * s.Sh + c.r2 * c.r2 * s.Shh;
+        c.nm1 = s.N - R(1);
+        c.l0 = 0;
+        c.l0 = value(c, R(0));
+        return c;
+    }
+    __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) {
+        const R us = c.us0 + y * c.rs, ut = c.ut0 + y * c.rt;
+        const R et = r_exp(ut), emt = R(1) / et, es = r_exp(us), em2 = R(1) / (es * es);
+        const R S = c.S0 + y * (R(2) * c.S1 + y * c.S2);
+        const R Sp = R(2) * (c.S1 + y * c.S2), Spp = R(2) * c.S2;
+        R l = -R(0.01) * et - ut - R(0.1) * es - c.nm1 * us - R(0.5) * em2 * S - c.l0;
+        R l1 = -R(0.01) * c.rt * et - c.rt - R(0.1) * c.rs * es - c.nm1 * c.rs - R(0.5) * em2 * (Sp - R(2) * c.rs * S);
+        R l2 = -R(0.01) * c.rt * c.rt * et - R(0.1) * c.rs * c.rs * es
+               - R(0.5) * em2 * (R(4) * c.rs * c.rs * S - R(4) * c.rs * Sp + Spp);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const R bk = k == 0 ? c.b1 + y * c.r1 : c.b2 + y * c.r2;
+            const R rk = k == 0 ? c.r1 : c.r2;
+            const R w = bk * emt;
+            const R wp = rk * emt - c.rt * w;
+            const R wpp = -c.rt * rk * emt - c.rt * wp;
+            const R den = R(5) + w * w;
+            const R f1 = -R(6) * w / den;
+            const R f2 = -R(6) * (R(5) - w * w) / (den * den);
+            l += student(w);
+            l1 += f1 * wp;
+            l2 += f2 * wp * wp + f1 * wpp;
+        }
+        return jet_guard<R>(l, l1, l2);
+    }
+    __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
+        const Stats s = stats(mp);
+        const R b1 = th[0], b2 = th[1], us = th[2], ut = th[3];
+        const R et = r_exp(ut), em2t = r_exp(-R(2) * ut), es = r_exp(us), em2 = r_exp(-R(2) * us);
+        const R ssr = s.See - R(2) * b1 * s.Se - R(2) * b2 * s.Seh + b1 * b1 * s.N + R(2) * b1 * b2 * s.Sh + b2 * b2 * s.Shh;
+        const R q1 = b1 * b1 * em2t, q2 = b2 * b2 * em2t;
+        if (g && lane == 0) {
+            g[0] = -R(6) * b1 * em2t / (R(5) + q1) + em2 * (s.Se - b1 * s.N - b2 * s.Sh);
+            g[1] = -R(6) * b2 * em2t / (R(5) + q2) + em2 * (s.Seh - b1 * s.Sh - b2 * s.Shh);
+            g[2] = -R(0.1) * es + R(1) - s.N + em2 * ssr;
+            g[3] = -R(0.01) * et - R(1) + R(6) * q1 / (R(5) + q1) + R(6) * q2 / (R(5) + q2);
+        }
+        return -R(0.01) * et - ut - R(3) * (r_log1p(q1 / R(5)) + r_log1p(q2 / R(5))) - R(0.1) * es + us - s.N * us
+               - R(0.5) * em2 * ssr;
+    }
+};
+
 }  // namespace klhr

@@ -475,5 +475,6 @@ KLHR_DECLARE_MODEL(corr_normal)
 KLHR_DECLARE_MODEL(ar1)
 KLHR_DECLARE_MODEL(ark)
 KLHR_DECLARE_MODEL(rosenbrock)
+KLHR_DECLARE_MODEL(earnings)
 
 }  // namespace klhr

@@ -56,12 +56,16 @@ class BSModel:
         theta = np.array(theta, dtype=np.float64)
         if self.name == "arK":
             theta[..., -1] = np.exp(theta[..., -1])
+        if self.name == "earnings":
+            theta[..., 2:] = np.exp(theta[..., 2:])
         return theta
 
     def unconstrain(self, theta):
         theta = np.array(theta, dtype=np.float64)
         if self.name == "arK":
             theta[..., -1] = np.log(theta[..., -1])
+        if self.name == "earnings":
+            theta[..., 2:] = np.log(theta[..., 2:])
         return theta
 
     def parameter_names(self):
@@ -70,6 +74,8 @@ class BSModel:
             return ["double_log_sigma"] + [f"alpha.{i + 1}" for i in range(m.Da)]
         if self.name == "arK":
             return ["alpha"] + [f"beta.{i + 1}" for i in range(m.K)] + ["sigma"]
+        if self.name == "earnings":
+            return ["beta.1", "beta.2", "sigma", "s"]
         if self.name == "rosenbrock":
             return [f"v.{i + 1}" for i in range(m.Dh)] + [f"theta.{i + 1}" for i in range(m.Dh)]
         return [f"y.{i + 1}" for i in range(m.dim())]

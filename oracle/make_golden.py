@@ -169,6 +169,9 @@ CASES = [
     ("rosenbrock_d4_sinh", "rosenbrock", {"D": 2}, "sinh", 1_000, dict(seed=72, overrelaxed=False), None),
     ("normal_d2_klhr_method2", "normal", {"D": 2}, "gauss", 1_500,
      dict(seed=81, eigen_method_one=False), None),
+    # the model of the reference's own self-tests (klhr.py:238) and relaxation experiment
+    ("earnings_klhr_tight", "earnings", "earnings.json", "gauss", 500, dict(seed=101, warmup=200), 1e-10),
+    ("earnings_sinh", "earnings", "earnings.json", "sinh", 250, dict(seed=102, warmup=100, overrelaxed=False), None),
     # long runs WITHOUT adaptation (warmup=0 -> isotropic direction law, identical on both
     # sides): only accept flags and thinned states are kept ("stats" tapes) for the
     # acceptance-rate and posterior parity tests.
@@ -236,6 +239,7 @@ def main():
             continue
         if isinstance(data, str):
             data = json.loads((ref / "stan" / data).read_text())
+            data = {k: v for k, v in data.items() if k != "male"}     # unused by stan/earnings.stan
         model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
         mod = ref_klhr if family == "gauss" else ref_sinh
         # "tight" tapes: same reference code, SciPy asked for a smaller gtol by rebinding

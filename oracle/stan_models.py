@@ -269,7 +269,63 @@ class Rosenbrock(StanModelBase):
         return -np.sum(rv * rv, axis=-1) - 50.0 * np.sum(2.0 * c1 * c1 + 4.0 * c0 * c2, axis=-1)
 
 
-MODEL_NAMES = ("normal", "ill-normal", "funnel", "corr-normal", "ar1", "arK", "rosenbrock")
+class Earnings(StanModelBase):
+    """reference stan/earnings.stan:1-17 -- the model of the reference's own self-tests
+    (klhr.py:238) and relaxation experiment.  Unconstrained [b1, b2, us = log sigma, ut = log s]:
+    lp = -0.01 e^ut + ut  - sum_k [ut + 3 log(1 + b_k^2 e^{-2ut} / 5)]  - 0.1 e^us + us
+         - N us - e^{-2us}/2 * sum_i (earn_i - b1 - b2 height_i)^2."""
+    name = "earnings"
+
+    def __init__(self, N, earn, height):
+        self.N = int(N)
+        self.e = np.asarray(earn, dtype=np.float64)
+        self.h = np.asarray(height, dtype=np.float64)
+        assert self.e.shape == (self.N,) and self.h.shape == (self.N,)
+
+    def dim(self):
+        return 4
+
+    def _resid(self, theta):
+        return self.e - theta[..., 0:1] - theta[..., 1:2] * self.h          # (..., N)
+
+    def lp_grad(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        b, us, ut = theta[..., :2], theta[..., 2], theta[..., 3]
+        r = self._resid(theta)
+        ssr = np.sum(r * r, axis=-1)
+        with np.errstate(all="ignore"):
+            q = b * b * np.exp(-2.0 * ut)[..., None]
+            em2 = np.exp(-2.0 * us)
+            lp = (-0.01 * np.exp(ut) + ut - 2.0 * ut - 3.0 * np.sum(np.log1p(q / 5.0), axis=-1)
+                  - 0.1 * np.exp(us) + us - self.N * us - 0.5 * em2 * ssr)
+            g = np.empty_like(theta)
+            g[..., 0] = -6.0 * b[..., 0] * np.exp(-2.0 * ut) / (5.0 + q[..., 0]) + em2 * np.sum(r, axis=-1)
+            g[..., 1] = -6.0 * b[..., 1] * np.exp(-2.0 * ut) / (5.0 + q[..., 1]) + em2 * np.sum(r * self.h, axis=-1)
+            g[..., 2] = -0.1 * np.exp(us) + 1.0 - self.N + em2 * ssr
+            g[..., 3] = -0.01 * np.exp(ut) - 1.0 + np.sum(6.0 * q / (5.0 + q), axis=-1)
+        return lp, g
+
+    def dir2(self, theta, rho):
+        b, us, ut = theta[..., :2], theta[..., 2], theta[..., 3]
+        rb, rs, rt = rho[..., :2], rho[..., 2], rho[..., 3]
+        r = self._resid(theta)
+        dr = -(rb[..., 0:1] + rb[..., 1:2] * self.h)
+        S = np.sum(r * r, axis=-1)
+        S1 = 2.0 * np.sum(r * dr, axis=-1)
+        S2 = 2.0 * np.sum(dr * dr, axis=-1)
+        with np.errstate(all="ignore"):
+            emt = np.exp(-ut)[..., None]
+            w = b * emt
+            w1 = rb * emt - rt[..., None] * w
+            w2 = -rt[..., None] * rb * emt - rt[..., None] * w1
+            f1 = -6.0 * w / (5.0 + w * w)
+            f2 = -6.0 * (5.0 - w * w) / (5.0 + w * w) ** 2
+            em2 = np.exp(-2.0 * us)
+            return (-0.01 * rt * rt * np.exp(ut) + np.sum(f2 * w1 * w1 + f1 * w2, axis=-1)
+                    - 0.1 * rs * rs * np.exp(us) - 0.5 * em2 * (4.0 * rs * rs * S - 2.0 * 2.0 * rs * S1 + S2))
+
+
+MODEL_NAMES = ("normal", "ill-normal", "funnel", "corr-normal", "ar1", "arK", "rosenbrock", "earnings")
 
 
 def make_model(name: str, data: dict) -> StanModelBase:
@@ -288,6 +344,8 @@ def make_model(name: str, data: dict) -> StanModelBase:
         return ARK(data["K"], data["T"], data["y"])
     if name == "rosenbrock":
         return Rosenbrock(data["D"])
+    if name == "earnings":
+        return Earnings(data["N"], data["earn"], data["height"])
     raise ValueError(f"unknown Stan model {name!r}; known: {MODEL_NAMES}")
 
 

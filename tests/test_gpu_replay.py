@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 GAUSS_TAPES = ["normal_d2_klhr", "normal_d2_klhr_method2", "illnormal_d100_klhr",
                "illnormal_d100_klhr_tight", "corrnormal_n50_klhr", "ar1_n100_klhr",
                "funnel_d2_klhr", "funnel_d2_klhr_tight", "funnel_d11_klhr_tight",
-               "ark_t200_klhr_tight", "rosenbrock_d4_klhr_tight"]
-SINH_TAPES = ["funnel_d2_sinh", "funnel_d2_sinh_tight", "ark_t200_sinh", "rosenbrock_d4_sinh"]
+               "ark_t200_klhr_tight", "rosenbrock_d4_klhr_tight", "earnings_klhr_tight"]
+SINH_TAPES = ["funnel_d2_sinh", "funnel_d2_sinh_tight", "ark_t200_sinh", "rosenbrock_d4_sinh", "earnings_sinh"]
 
 
 def _run(name, dtype, force_octet=False):
@@ -41,8 +41,9 @@ def test_gauss_family_fp64_1e10(name, force_octet):
     assert np.allclose(gpu["theta"], ref["theta"], rtol=tol, atol=tol)
 
 
-@pytest.mark.parametrize("name,force_octet", KERNELS)
+@pytest.mark.parametrize("name,force_octet", [k for k in KERNELS if not k[0].startswith("earnings")])
 def test_gauss_family_fp32_1e4(name, force_octet):
+    # (earnings is excluded: dollar-scale residual sums of ~1e12 are outside what fp32 can carry)
     t, gpu, ref, (em, es, ez, er) = _run(name, torch.float32, force_octet)
     tol = 1e-4
     # fp32 round-off occasionally flips a back-tracking decision on the non-Gaussian targets:

@@ -279,7 +279,7 @@ def test_sampler_api_matches_reference_surface():
     assert d.shape == (10, 64, 2) and b._draw == 27 and torch.equal(d[-1], b.theta)
     assert kb.KLHRSINH(model)._fit.overrelax_K == 10 and kb.KLHR(model)._fit.overrelax_K == 0   # reference defaults
     with pytest.raises(NotImplementedError):
-        kb.BSModel(stan_file="stan/earnings.stan", data={})
+        kb.BSModel(stan_file="stan/garch.stan", data={})      # not among the implemented targets
 
 
 def test_adaptation_learns_scales_and_leading_direction():
@@ -306,7 +306,9 @@ def test_model_eval_matches_oracle():
     y = stan_models.simulate_ark_series(T=300, seed=5)
     cases = [("normal", {"D": 5}), ("ill-normal", {"D": 33}), ("funnel", {"D": 6}),
              ("corr-normal", {"N": 20, "rho": 0.9}), ("ar1", {"N": 17}),
-             ("arK", {"K": 5, "T": 300, "y": y.tolist()}), ("rosenbrock", {"D": 3})]
+             ("arK", {"K": 5, "T": 300, "y": y.tolist()}), ("rosenbrock", {"D": 3}),
+             ("earnings", {"N": 50, "earn": (3 + rng.normal(size=50)).tolist(),
+                           "height": (66 + 4 * rng.normal(size=50)).tolist()})]
     for name, data in cases:
         m = kb.BSModel(stan_file=f"stan/{name}.stan", data=data, device=device())
         om = stan_models.make_model(name, data)

@@ -40,7 +40,7 @@ def test_gaussian_targets(tapes, name, tol_m, tol_s):
 # fits may sit in a different local optimum than SciPy's; the bulk agrees at 1e-7.
 @pytest.mark.parametrize("name,frac", [
     ("funnel_d2_klhr_tight", 0.995), ("funnel_d11_klhr_tight", 0.995),
-    ("ark_t200_klhr_tight", 0.995), ("rosenbrock_d4_klhr_tight", 0.985)])
+    ("ark_t200_klhr_tight", 0.995), ("rosenbrock_d4_klhr_tight", 0.985), ("earnings_klhr_tight", 0.98)])
 def test_nongaussian_targets_gaussian_family(tapes, name, frac):
     t, out, em, es = _run(tapes, name)
     good = (em <= 1e-6) & (es <= 1e-6)
@@ -48,7 +48,7 @@ def test_nongaussian_targets_gaussian_family(tapes, name, frac):
     assert out["converged"].mean() >= 0.995
     assert np.array_equal(out["accept"][good], t["accept"][good])
     fin = good & np.isfinite(t["r"])
-    assert np.allclose(out["r"][fin], t["r"][fin], rtol=0, atol=1e-5)
+    assert np.allclose(out["r"][fin], t["r"][fin], rtol=1e-6, atol=1e-5)   # rtol: lp is ~1e11 on earnings
     assert np.median(em) <= 1e-9 and np.median(es) <= 1e-9
 
 

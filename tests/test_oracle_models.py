@@ -9,11 +9,13 @@ from oracle import stan_models as sm
 def _models():
     rng = np.random.default_rng(5)
     y = sm.simulate_ark_series(T=120, seed=3)
+    h = 66.0 + 4.0 * rng.normal(size=80)
+    e = 3.0 + 0.5 * (h - 66.0) + 2.0 * rng.normal(size=80)
     return [sm.Normal(3), sm.IllNormal(7), sm.Funnel(1), sm.Funnel(4), sm.CorrNormal(6, 0.9),
-            sm.AR1(8), sm.ARK(5, 120, y), sm.Rosenbrock(2)], rng
+            sm.AR1(8), sm.ARK(5, 120, y), sm.Rosenbrock(2), sm.Earnings(80, e, h)], rng
 
 
-@pytest.mark.parametrize("idx", range(8))
+@pytest.mark.parametrize("idx", range(9))
 def test_gradient_and_dir2_match_finite_differences(idx):
     models, rng = _models()
     m = models[idx]
