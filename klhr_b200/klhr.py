@@ -247,6 +247,48 @@ class KLHR(MCMCBase):
         eta = tr.eta[0]
         return eta[0].double().cpu().numpy() if self.chains == 1 else eta
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to continue the run bit for bit: the RNG is counter based (a function of
+        seed, chain id and draw index), so no generator state has to be saved.  (The reference has no
+        checkpointing; its parquet dumps are commented out.)"""
+        mom, gmom, pca = self._onlinemoments, self._onlinemoments_density, self._onlinepca
+        return {
+            "theta": self._theta.detach().cpu().clone(), "seed": self.seed, "draw": self._draw,
+            "chain_offset": self._chain_offset, "K": self.K, "acc_seen": self._acc_seen,
+            "accept_count": self._accept_count.cpu().clone(), "evals_total": self._evals_total.cpu().clone(),
+            "mean": np.array(self._mean), "cov": np.array(self._cov), "eigvecs": np.array(self._eigvecs),
+            "eigvals": np.array(self._eigvals),
+            "moments": [(m.N, m.s1.cpu().clone(), m.s2.cpu().clone(), m.shift.cpu().clone()) for m in (mom, gmom)],
+            "pca": (pca.n, pca.outer.cpu().clone()),
+            "smoothK": (self._smoothK._x, self._smoothK._count),
+        }
+
+    def load_state_dict(self, sd):
+        if tuple(sd["theta"].shape) != (self.chains, self.D):
+            raise ValueError("checkpoint shape does not match this sampler")
+        dev = self.device
+        self._theta.copy_(sd["theta"].to(dev, self.dtype))
+        self.seed, self._draw, self._chain_offset = int(sd["seed"]), int(sd["draw"]), int(sd["chain_offset"])
+        self.K, self._acc_seen = int(sd["K"]), float(sd["acc_seen"])
+        if self._fit.overrelax_K:
+            self._fit.overrelax_K = self.K
+        self._accept_count.copy_(sd["accept_count"].to(dev))
+        self._evals_total.copy_(sd["evals_total"].to(dev))
+        self._mean, self._cov = np.array(sd["mean"]), np.array(sd["cov"])
+        self._eigvecs, self._eigvals = np.array(sd["eigvecs"]), np.array(sd["eigvals"])
+        for m, (n, s1, s2, shift) in zip((self._onlinemoments, self._onlinemoments_density), sd["moments"]):
+            m.N = int(n)
+            m.s1.copy_(s1.to(dev))
+            m.s2.copy_(s2.to(dev))
+            m.shift = shift.to(dev, torch.float64).clone()
+        self._onlinepca.n = int(sd["pca"][0])
+        self._onlinepca.outer.copy_(sd["pca"][1].to(dev))
+        self._onlinepca._eig = None
+        self._smoothK._x, self._smoothK._count = sd["smoothK"]
+        self._shift_dev = torch.as_tensor(self._mean, dtype=self.dtype, device=dev).contiguous()
+        self._refresh_direction()
+
     @property
     def acceptance_probability(self):
         """Mean accept rate over all chains and draws (running mean of klhr.py:192-193)."""
