@@ -58,6 +58,9 @@ typedef struct klhr_model {
  * kernels (tile kernel: diagonal-Gaussian targets with the Gaussian family; chain kernel: every
  * other case whose rho tile fits in shared memory) apply -- the parity tests cover both paths */
 #define KLHR_FIT_FORCE_OCTET 1
+/* sinh family with the tail-weight parameter frozen at d = 1: the 3-parameter variant of reference
+ * sub_klhr_sinh.py (SUBKLHRSINH); eta is still reported as (m, log s, 0, e) */
+#define KLHR_FIT_FIX_D 2
 
 /* Line-fit configuration: the reference's constructor arguments that reach the fit
  * (klhr.py:16-49 / klhr_sinh.py:15-47) plus the fixed iteration budget that replaces

@@ -14,6 +14,7 @@ __all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "
 try:  # samplers (import kept soft only so that partial checkouts still expose the engine)
     from .klhr import KLHR
     from .klhr_sinh import KLHRSINH
-    __all__ += ["KLHR", "KLHRSINH"]
+    from .sub_klhr_sinh import SUBKLHRSINH
+    __all__ += ["KLHR", "KLHRSINH", "SUBKLHRSINH"]
 except ImportError:  # pragma: no cover
     pass

@@ -70,6 +70,7 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     fp.kmax = (f->kmax > 0 && f->kmax < 1 + f->n2 * f->nb) ? f->kmax : 1 + f->n2 * f->nb;
     if (f->overrelax_K < 0 || f->overrelax_K > 50) return fail(-8, "overrelax_K must be in 0..50 (klhr.py:213)");
     fp.or_K = f->overrelax_K;
+    fp.fix_d = (f->flags & KLHR_FIT_FIX_D) ? 1 : 0;
     fp.initscale = f->initscale; fp.tol = f->tol; fp.scale_clip = f->scale_clip;
     fp.gtol1 = f->gtol1; fp.gtol2 = f->gtol2; fp.step_cap = f->step_cap; fp.c1 = f->c1; fp.basin = f->basin;
     for (int i = 0; i < kMaxNodes; ++i) {

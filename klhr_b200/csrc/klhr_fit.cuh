@@ -21,6 +21,7 @@ struct FitParams {
     int n1, n2, nb;        // stage-1 iterations, stage-2 Newton steps, halvings per step
     int kmax;              // cap on stage-2 KL evaluations
     int or_K;              // > 0: over-relaxed proposal with K trials (klhr.py:160-173)
+    int fix_d;             // sinh family with d = 1 frozen (sub_klhr_sinh.py)
     double initscale, tol, scale_clip;
     double gtol1, gtol2, step_cap, c1, basin;
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
@@ -234,7 +235,7 @@ __device__ __forceinline__ SinhPar<R> sinh_unpack(const R (&eta)[4], const FitPa
     SinhPar<R> q;
     q.m = eta[0];
     q.s = r_exp(r_clamp(eta[1], -c, c)) + tol;
-    q.d = r_exp(r_clamp(eta[2], -c, c)) + tol;
+    q.d = fp.fix_d ? R(1) : r_exp(r_clamp(eta[2], -c, c)) + tol;      // sub_klhr_sinh.py:92-97: no d
     q.e = eta[3];
     return q;
 }
@@ -292,6 +293,9 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
     h00 = grp_sum<G>(h00, m); h01 = grp_sum<G>(h01, m); h02 = grp_sum<G>(h02, m); h03 = grp_sum<G>(h03, m);
     h11 = grp_sum<G>(h11, m); h12 = grp_sum<G>(h12, m); h13 = grp_sum<G>(h13, m);
     h22 = grp_sum<G>(h22, m); h23 = grp_sum<G>(h23, m); h33 = grp_sum<G>(h33, m);
+    if (fp.fix_d) {                    // d frozen: its row and column drop out of the Newton system
+        g2 = 0; h02 = 0; h12 = 0; h23 = 0; h22 = 1;
+    }
     const R s = q.s;
     S.g[0] = g0 * s; S.g[1] = g1; S.g[2] = g2; S.g[3] = g3;
     S.H[0][0] = h00 * s * s;
@@ -499,6 +503,10 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
     if constexpr (n == 4) {
         eta[2] = init2 * (R)fp.initscale;          // klhr_sinh.py:191-193
         eta[3] = init3 * (R)fp.initscale;
+        if (fp.fix_d) {                             // sub_klhr_sinh.py:184-186: start (xi, log s, e)
+            eta[3] = eta[2];
+            eta[2] = 0;
+        }
     }
     bool conv;
     stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv);

@@ -41,6 +41,7 @@ class FitConfig:
     nb: int = 8
     kmax: int = 0                      # cap on stage-2 KL evaluations (0: 1 + n2 * nb)
     overrelax_K: int = 0               # K > 0: over-relaxed proposals with K trials (klhr.py:160-173)
+    fix_d: bool = False                # sinh family with d = 1 frozen (reference sub_klhr_sinh.py)
     gtol1: float = 1e-8
     gtol2: float = 1e-10
     step_cap: float = 2.0
@@ -70,7 +71,7 @@ class FitConfig:
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin, flags=1 if self.force_octet else 0, kmax=int(self.kmax),
+                         basin=self.basin, flags=(1 if self.force_octet else 0) | (2 if self.fix_d else 0), kmax=int(self.kmax),
                          overrelax_K=int(self.overrelax_K))
         for i in range(self.N):
             d.x[i] = float(self.x[i])

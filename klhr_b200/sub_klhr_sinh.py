@@ -1,0 +1,20 @@
+"""``SUBKLHRSINH`` -- KL Hit-and-Run with the 3-parameter sinh-arcsinh family (d = 1).
+
+Drop-in for reference ``sub_klhr_sinh.py:14-284``: the same step as ``KLHRSINH`` with the tail-weight
+parameter removed (eta = (m, log s, e), ``sub_klhr_sinh.py:92-97``).  On the device this is the sinh
+kernel with ``KLHR_FIT_FIX_D``: d = 1 exactly and its row/column dropped from the Newton system.
+``fit`` returns 3-vectors like the reference.
+"""
+from __future__ import annotations
+
+from .klhr_sinh import KLHRSINH
+
+
+class SUBKLHRSINH(KLHRSINH):
+    def __init__(self, bsmodel, *args, **kwargs):
+        super().__init__(bsmodel, *args, **kwargs)
+        self._fit.fix_d = True
+
+    def fit(self, rho, z_init=None):
+        eta = super().fit(rho, z_init=z_init)
+        return eta[..., [0, 1, 3]]

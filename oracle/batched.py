@@ -45,6 +45,7 @@ class FitConfig:
     n2: int = 24                     # stage-2 iteration budget (Newton steps)
     nb: int = 8                      # back-tracking halvings per Newton step
     kmax: int = 0                    # cap on stage-2 KL evaluations per fit (0: 1 + n2 * nb)
+    fix_d: bool = False              # sinh family with d = 1 frozen (reference sub_klhr_sinh.py)
     gtol1: float = 1e-8              # |l'| / sqrt(-l'') at the mode
     gtol2: float = 1e-10             # inf-norm of the scaled KL gradient
     step_cap: float = 2.0            # inf-norm cap of a stage-2 step in scaled coordinates
@@ -180,6 +181,8 @@ def _sinh_unpack(eta, cfg):
     with np.errstate(all="ignore"):
         s = np.exp(np.clip(eta[:, 1], -c, c)) + cfg.tol
         d = np.exp(np.clip(eta[:, 2], -c, c)) + cfg.tol
+    if cfg.fix_d:                                               # sub_klhr_sinh.py:92-97
+        d = np.ones_like(s)
     return eta[:, 0], s, d, eta[:, 3]
 
 
@@ -225,6 +228,11 @@ def _kl_sinh(model, theta, rho, eta, x, w, cfg):
         HL[..., 3, 3] = -sech2 * invd * invd
         H = np.sum(w[None, :, None, None] * (HL - l2[..., None, None] * gT[..., :, None] * gT[..., None, :]
                                              - l1[..., None, None] * HT), axis=1)
+        if cfg.fix_d:                  # d frozen: its row and column drop out of the Newton system
+            g[:, 2] = 0.0
+            H[:, 2, :] = 0.0
+            H[:, :, 2] = 0.0
+            H[:, 2, 2] = 1.0
         # scale coordinate 0 by s
         g[:, 0] *= s
         H[:, 0, :] *= s[:, None]
@@ -409,6 +417,9 @@ def fit(model, theta, rho, z_init, cfg: FitConfig, init4=None, xw=None):
         eta0[:, 0] = xi
         eta0[:, 1] = tau0
         eta0[:, 2:] = init4[:, 2:] * cfg.initscale           # klhr_sinh.py:191-193
+        if cfg.fix_d:                                        # sub_klhr_sinh.py:184-186
+            eta0[:, 3] = eta0[:, 2]
+            eta0[:, 2] = 0.0
     eta, nev2, conv = stage2_newton(model, theta, rho, eta0, cfg, x, w)
     return eta, nev1 + nev2 * cfg.N, conv
 

@@ -73,7 +73,7 @@ def _tape_run(algo, M, family):
     """Drive ``algo.draw()`` M times, capturing inputs/outputs of every step."""
     rec = {k: [] for k in ("theta0", "rho", "z_init", "z_prop", "u", "eta", "zp", "r",
                            "accept", "theta1", "grad_evals_draw", "ujdir")}
-    if family == "sinh":
+    if family in ("sinh", "subsinh"):
         rec["init4"] = []
     closures = {"draw": [], "mean": [], "cov": [], "eigvecs": [], "eigvals": []}
     cur = {}
@@ -86,15 +86,18 @@ def _tape_run(algo, M, family):
         cur["rho"] = np.array(rho, copy=True)
         ge0 = algo.grad_evals
         n0 = len(algo.rng.log)
-        eta = orig_fit(rho)
+        eta = eta_ret = orig_fit(rho)
         # variates consumed inside fit: 1 normal (stage-1 start) [+ normal(size=4) for sinh]
         used = algo.rng.log[n0:]
         cur["z_init"] = float(used[0][1])
         if family == "sinh":
             cur["init4"] = np.array(used[1][1], copy=True)
+        if family == "subsinh":                       # normal(size=3): (.., .., e start); padded to 4
+            cur["init4"] = np.append(np.array(used[1][1], copy=True), 0.0)
+            eta = np.array([eta[0], eta[1], 0.0, eta[2]])      # stored as (m, log s, log d = 0, e)
         cur["eta"] = np.array(eta, copy=True)
         cur["nfev"] = algo.grad_evals - ge0
-        return eta
+        return eta_ret
 
     def mh(eta, rho):
         theta0 = np.array(algo.theta, copy=True)
@@ -169,6 +172,9 @@ CASES = [
     ("rosenbrock_d4_sinh", "rosenbrock", {"D": 2}, "sinh", 1_000, dict(seed=72, overrelaxed=False), None),
     ("normal_d2_klhr_method2", "normal", {"D": 2}, "gauss", 1_500,
      dict(seed=81, eigen_method_one=False), None),
+    # 3-parameter sinh-arcsinh variant (reference sub_klhr_sinh.py)
+    ("funnel_d2_subsinh_tight", "funnel", {"D": 1}, "subsinh", 1_000, dict(seed=111, overrelaxed=False), 1e-9),
+    ("rosenbrock_d4_subsinh", "rosenbrock", {"D": 2}, "subsinh", 400, dict(seed=112, overrelaxed=False), None),
     # the model of the reference's own self-tests (klhr.py:238) and relaxation experiment
     ("earnings_klhr_tight", "earnings", "earnings.json", "gauss", 500, dict(seed=101, warmup=200), 1e-10),
     ("earnings_sinh", "earnings", "earnings.json", "sinh", 250, dict(seed=102, warmup=100, overrelaxed=False), None),
@@ -212,6 +218,7 @@ def main():
     import bsmodel as shim
     import klhr as ref_klhr
     import klhr_sinh as ref_sinh
+    import sub_klhr_sinh as ref_sub
     import scipy.optimize
 
     out_dir = Path(args.out)
@@ -241,7 +248,7 @@ def main():
             data = json.loads((ref / "stan" / data).read_text())
             data = {k: v for k, v in data.items() if k != "male"}     # unused by stan/earnings.stan
         model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
-        mod = ref_klhr if family == "gauss" else ref_sinh
+        mod = {"gauss": ref_klhr, "sinh": ref_sinh, "subsinh": ref_sub}[family]
         # "tight" tapes: same reference code, SciPy asked for a smaller gtol by rebinding
         # the module-level name the reference calls (klhr.py:5); sinh passes its own gtol
         # through options (klhr_sinh.py:199) so it is overridden there.
@@ -253,7 +260,7 @@ def main():
             mod.minimize = tight
         else:
             mod.minimize = scipy.optimize.minimize
-        cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
+        cls = {"gauss": ref_klhr.KLHR, "sinh": ref_sinh.KLHRSINH, "subsinh": ref_sub.SUBKLHRSINH}[family]
         seed = kw.pop("seed")
         kw = dict(kw)
         # construct with a plain seed (the ctor draws the start point), then tape

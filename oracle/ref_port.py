@@ -164,6 +164,82 @@ class SinhLine:
         return ld
 
 
+class SubSinhLine(SinhLine):
+    """3-parameter sinh-arcsinh family (d = 1); eta = (m, log s, e).
+    reference ``sub_klhr_sinh.py:92-169,226-233`` -- same maths as SinhLine with d removed; the
+    model gradient is clipped with ``grad_clip`` here (:152-154)."""
+    n_eta = 3
+
+    def __init__(self, x, w, tol, scale_clip, grad_clip=1e15):
+        super().__init__(x, w, tol, scale_clip)
+        self.grad_clip = grad_clip
+
+    def unpack(self, eta):
+        return eta[0], np.exp(np.clip(eta[1], -self.clip, self.clip)) + self.tol, eta[2]
+
+    def transport(self, x, eta):
+        m, s, e = self.unpack(eta)
+        return m + s * np.sinh(self._cl(np.arcsinh(x) + e))
+
+    def transport_inv(self, x, eta):
+        m, s, e = self.unpack(eta)
+        return np.sinh(self._cl(np.arcsinh((x - m) / s) - e))
+
+    def grad_transport(self, x, eta):
+        m, s, e = self.unpack(eta)
+        g = np.ones(3)
+        a = np.arcsinh(x) + e
+        g[1] = s * np.sinh(self._cl(a))
+        g[2] = s * np.cosh(self._cl(a))
+        return g
+
+    def log_abs_jac(self, x, eta):
+        _, _, e = self.unpack(eta)
+        out = -eta[1]
+        out -= np.log(np.cosh(self._cl(np.arcsinh(x) + e)))
+        return out
+
+    def grad_log_abs_jac(self, x, eta):
+        _, _, e = self.unpack(eta)
+        g = np.zeros(3)
+        g[1] = -1
+        g[2] = -np.tanh(self._cl(np.arcsinh(x) + e))
+        return g
+
+    def model_grad(self, model, theta):
+        lp, g = model.log_density_gradient(theta)
+        return lp, np.clip(g, -self.grad_clip, self.grad_clip)
+
+    def kl(self, eta, theta, rho, model):
+        acc = 0.0
+        g = np.zeros(3)
+        for xn, wn in zip(self.x, self.w):
+            t = self.transport(xn, eta)
+            lp, glp = self.model_grad(model, t * rho + theta)
+            laj = self.log_abs_jac(xn, eta)
+            acc += wn * (laj - lp)
+            glaj = self.grad_log_abs_jac(xn, eta)
+            gT = self.grad_transport(xn, eta)
+            g -= wn * glp.dot(rho) * gT
+            g += wn * glaj
+        return acc, g
+
+    def stage2_start(self, xi_hat, half_log_s2, rng, initscale):
+        init = rng.normal(size=3) * initscale
+        init[0] = xi_hat
+        init[1] = half_log_s2
+        return init
+
+    def logq(self, x, eta):
+        m, s, e = self.unpack(eta)
+        ld = -0.5 * self.transport_inv(x, eta) ** 2
+        z = (x - m) / s
+        ld += np.log(np.cosh(self._cl(np.arcsinh(z) - e)))
+        ld -= eta[1]
+        ld -= 0.5 * np.log1p(z * z)
+        return ld
+
+
 class ChainSampler:
     """One chain of KLHR (family="gauss") or KLHRSINH (family="sinh").
 
@@ -191,7 +267,8 @@ class ChainSampler:
         self.J = (J if J < self.D else self.D - 1) if gauss else J     # klhr.py:39 vs klhr_sinh.py:37
         self.tol, self.initscale = tol, initscale
         self.x, self.w = gauss_hermite_probabilists(N)
-        self.line = (GaussLine if gauss else SinhLine)(self.x, self.w, tol, scale_clip)
+        self.line = {"gauss": GaussLine, "sinh": SinhLine, "subsinh": SubSinhLine}[family](
+            self.x, self.w, tol, scale_clip)
         self.schedule = WindowSchedule(warmup, windowsize, windowscale)
         self.mom_theta = RunningMoments(self.D)
         self.mom_grad = RunningMoments(self.D)
@@ -355,8 +432,8 @@ class ReplayRNG:
         if self.family == "gauss":
             z = self.t["z_init"][self.i] if k % 2 == 0 else np.array([self.t["z_prop"][self.i]])
         else:
-            z = (self.t["z_init"][self.i], self.t["init4"][self.i],
-                 np.array([self.t["z_prop"][self.i]]))[k % 3]
+            start = self.t["init4"][self.i] if self.family == "sinh" else self.t["init4"][self.i][:3]
+            z = (self.t["z_init"][self.i], start, np.array([self.t["z_prop"][self.i]]))[k % 3]
         return loc + scale * z
 
     def uniform(self):

@@ -16,6 +16,9 @@ def up(a, dtype=torch.float64):
 
 def fit_pair(family, dtype=torch.float64, **kw):
     """(klhr_b200.FitConfig, oracle FitConfig) with identical settings."""
+    if family == "subsinh":
+        family = "sinh"
+        kw = dict(kw, fix_d=True)
     if family == "sinh":
         base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32)
     else:
@@ -23,7 +26,7 @@ def fit_pair(family, dtype=torch.float64, **kw):
     base.update(kw)
     k = kb.FitConfig(**base).for_dtype(dtype)
     o = batched.FitConfig(**{f: getattr(k, f) for f in
-                             ("family", "N", "initscale", "tol", "scale_clip", "n1", "n2", "nb", "kmax", "gtol1",
+                             ("family", "N", "initscale", "tol", "scale_clip", "n1", "n2", "nb", "kmax", "fix_d", "gtol1",
                               "gtol2", "step_cap", "c1", "basin")})
     if dtype == torch.float32:
         o.eps = float(np.finfo(np.float32).eps)

@@ -282,6 +282,21 @@ def test_sampler_api_matches_reference_surface():
         kb.BSModel(stan_file="stan/garch.stan", data={})      # not among the implemented targets
 
 
+def test_sub_klhr_sinh_class():
+    """reference sub_klhr_sinh.py: 3-parameter family; fit returns (m, log s, e); funnel x ~ N(0, 9)."""
+    model = kb.BSModel(stan_file="stan/funnel.stan", data={"D": 1}, device=device())
+    s = kb.SUBKLHRSINH(model, seed=2, chains=4096, warmup=0, overrelaxed=False)
+    rho = np.array([[1.0, 0.0]])
+    assert tuple(s.fit(rho).shape) == (4096, 3)
+    s.run(1500)
+    S = 1000
+    s1, s2 = s.run(S, chain_stats=True)
+    summ = chain_summary(s1, s2, S)
+    assert abs(float(summ["mean"][0])) < 5 * float(summ["mcse_mean"][0]) + 0.03
+    assert abs(float(summ["var"][0]) - 9.0) < 5 * float(summ["mcse_var"][0]) + 0.3
+    assert 0.85 < s.acceptance_probability < 1.0
+
+
 def test_checkpoint_resume_is_bit_exact(tmp_path):
     """run(a) ; save ; load into a fresh sampler ; run(b)  ==  run(a + b), across a window closure and for
     both the accumulating and the fast kernels (counter-based RNG: no generator state to save)."""

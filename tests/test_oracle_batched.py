@@ -11,7 +11,8 @@ from oracle.batched import FitConfig
 def _run(tapes, name):
     t, meta, data = tapes(name)
     model = stan_models.make_model(meta["model"], data)
-    cfg = FitConfig.for_family(meta["family"])
+    cfg = (FitConfig.for_family("sinh", fix_d=True) if meta["family"] == "subsinh"
+           else FitConfig.for_family(meta["family"]))
     out = batched.step(model, t["theta0"], t["rho"], t["z_init"], t["z_prop"], t["u"], cfg,
                        init4=t.get("init4"), xw=(t["x_nodes"], t["w_nodes"]))
     s = np.exp(t["eta"][:, 1])
@@ -60,7 +61,7 @@ def test_funnel_default_gtol_tape(tapes):
     assert (out["accept"] != t["accept"]).mean() <= 0.002
 
 
-@pytest.mark.parametrize("name", ["funnel_d2_sinh_tight"])
+@pytest.mark.parametrize("name", ["funnel_d2_sinh_tight", "funnel_d2_subsinh_tight"])
 def test_sinh_family_bulk_agreement(tapes, name):
     t, out, em, es = _run(tapes, name)
     good = (em <= 1e-5) & (es <= 1e-5)
