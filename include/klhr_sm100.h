@@ -162,6 +162,14 @@ int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direct
              int32_t n_steps, uint64_t seed, const klhr_accum_t* accum, const klhr_trace_t* trace,
              void* stream);
 
+/* Random-walk Metropolis (reference mh.py:7-37, the comparison sampler of experiment_accuracy.py:69) on
+ * the same engine: n_steps draws theta' = theta + stepsize N(0, I) per chain with the chain's Philox
+ * stream.  accum: accept_count, draws/thin, chain_s1/chain_s2 are honoured; trace: rho receives xi,
+ * plus r, accept, u. */
+int klhr_mh_run(const klhr_model_t* model, int dtype, void* theta_dev, double stepsize, int64_t n_chains,
+                int64_t chain_offset, int64_t draw_offset, int32_t n_steps, uint64_t seed,
+                const klhr_accum_t* accum, const klhr_trace_t* trace, void* stream);
+
 /* Pooled second-moment accumulation for the adaptation PCA (replaces the per-sample CCIPCA
  * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,
  * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype. */

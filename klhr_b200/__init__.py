@@ -15,6 +15,7 @@ try:  # samplers (import kept soft only so that partial checkouts still expose t
     from .klhr import KLHR
     from .klhr_sinh import KLHRSINH
     from .sub_klhr_sinh import SUBKLHRSINH
-    __all__ += ["KLHR", "KLHRSINH", "SUBKLHRSINH"]
+    from .mh import MH
+    __all__ += ["KLHR", "KLHRSINH", "SUBKLHRSINH", "MH"]
 except ImportError:  # pragma: no cover
     pass

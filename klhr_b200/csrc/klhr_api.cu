@@ -7,6 +7,7 @@
 #include <string>
 
 #include "klhr_chain.cuh"
+#include "klhr_mh.cuh"
 
 namespace klhr {
 
@@ -288,6 +289,37 @@ int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direct
     a.chain_offset = chain_offset; a.draw_offset = draw_offset; a.n_steps = n_steps; a.seed = seed;
     return cuda_fail(dispatch_step(a, dtype, fit->family, false, use_acc, (cudaStream_t)stream, nullptr, fit->flags),
                      "klhr_run");
+}
+
+int klhr_mh_run(const klhr_model_t* model, int dtype, void* theta_dev, double stepsize, int64_t n_chains,
+                int64_t chain_offset, int64_t draw_offset, int32_t n_steps, uint64_t seed, const klhr_accum_t* accum,
+                const klhr_trace_t* trace, void* stream) {
+    MhArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains < 0 || n_steps < 0 || chain_offset < 0 || draw_offset < 0) return fail(-10, "negative count or offset");
+    if (!(stepsize > 0)) return fail(-14, "stepsize must be positive");
+    if (n_chains == 0 || n_steps == 0) return 0;
+    if (!theta_dev) return fail(-1, "theta must not be NULL");
+    a.theta = theta_dev; a.B = n_chains; a.stepsize = stepsize;
+    a.chain_offset = chain_offset; a.draw_offset = draw_offset; a.n_steps = n_steps; a.seed = seed;
+    a.acc.thin = 1;
+    if (accum) { a.acc = *accum; if (a.acc.thin < 1) a.acc.thin = 1; }
+    if (trace) a.tr = *trace;
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = -2;
+    switch (a.mp.id) {
+        case KLHR_MODEL_NORMAL: e = launch_mh_normal(a, dtype, st); break;
+        case KLHR_MODEL_ILL_NORMAL: e = launch_mh_ill_normal(a, dtype, st); break;
+        case KLHR_MODEL_FUNNEL: e = launch_mh_funnel(a, dtype, st); break;
+        case KLHR_MODEL_CORR_NORMAL: e = launch_mh_corr_normal(a, dtype, st); break;
+        case KLHR_MODEL_AR1: e = launch_mh_ar1(a, dtype, st); break;
+        case KLHR_MODEL_ARK: e = launch_mh_ark(a, dtype, st); break;
+        case KLHR_MODEL_ROSENBROCK: e = launch_mh_rosenbrock(a, dtype, st); break;
+        case KLHR_MODEL_EARNINGS: e = launch_mh_earnings(a, dtype, st); break;
+    }
+    return cuda_fail(e, "klhr_mh_run");
 }
 
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running, int accumulate,

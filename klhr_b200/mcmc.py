@@ -34,7 +34,7 @@ class MCMCBase:
         else:
             th = np.asarray(theta.detach().cpu() if torch.is_tensor(theta) else theta, dtype=np.float64)
             th = np.broadcast_to(th.reshape(-1, self.D), (self.chains, self.D))
-        self._theta = torch.as_tensor(np.ascontiguousarray(th), dtype=dtype, device=self.device).contiguous()
+        self._theta = torch.as_tensor(np.array(th, dtype=np.float64, order="C"), dtype=dtype, device=self.device).contiguous()
 
     # ``theta``: (D,) NumPy for one chain like the reference, else the live (B, D) device tensor
     @property

@@ -200,6 +200,9 @@ FREERUNS = [
     ("freerun_funnel_d2_klhr_overrelaxed", "funnel", {"D": 1}, "gauss", 150, dict(seed=4, warmup=0, overrelaxed=True)),
     ("freerun_funnel_d2_sinh_overrelaxed", "funnel", {"D": 1}, "sinh", 120, dict(seed=5, warmup=0, overrelaxed=True)),
     ("freerun_illnormal_d20_klhr_adapt", "ill-normal", {"D": 20}, "gauss", 130, dict(seed=6, warmup=100)),
+    # random-walk Metropolis (reference mh.py), stepsize of experiment_accuracy.py:69
+    ("freerun_normal_d2_mh", "normal", {"D": 2}, "mh", 3000, dict(seed=7, stepsize=0.09)),
+    ("freerun_funnel_d2_mh", "funnel", {"D": 1}, "mh", 3000, dict(seed=8, stepsize=0.9)),
 ]
 
 
@@ -228,16 +231,20 @@ def main():
         if args.only and args.only not in name:
             continue
         model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
-        cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
-        (ref_klhr if family == "gauss" else ref_sinh).minimize = scipy.optimize.minimize
-        algo = cls(model, **kw)
+        if family == "mh":
+            import mh as ref_mh
+            algo = ref_mh.MH(model, kw["stepsize"], seed=kw["seed"])
+        else:
+            cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
+            (ref_klhr if family == "gauss" else ref_sinh).minimize = scipy.optimize.minimize
+            algo = cls(model, **kw)
         np.random.seed(kw["seed"])                      # SciPy's global RNG (over-relaxed proposals)
         thetas = np.array([algo.draw() for _ in range(M)])
         meta = dict(case=name, model=stem, family=family, draws=M, ctor=kw, numpy=np.__version__,
                     scipy=scipy.__version__)
         np.savez_compressed(out_dir / f"{name}.npz", thetas=thetas,
                             acceptance_probability=np.array(float(np.ravel(algo.acceptance_probability)[0])),
-                            grad_evals=np.array(int(algo.grad_evals)), meta_json=np.array(json.dumps(meta)),
+                            grad_evals=np.array(int(getattr(algo, "grad_evals", 0))), meta_json=np.array(json.dumps(meta)),
                             data_json=np.array(json.dumps(data)))
         print(f"{name:36s} draws={M:6d} acc={float(np.ravel(algo.acceptance_probability)[0]):.3f}")
 

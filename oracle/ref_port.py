@@ -407,6 +407,35 @@ class ChainSampler:
         return out
 
 
+class MHChain:
+    """Random-walk Metropolis, one chain: port of reference ``mh.py:7-37`` (``stepsize * N(0, I)``
+    proposal, symmetric-proposal terms kept like the reference so the arithmetic is identical)."""
+
+    def __init__(self, model, stepsize, seed=None, theta=None):
+        self.model, self.D, self.stepsize = model, model.dim(), stepsize
+        self.rng = np.random.default_rng(seed)
+        self.theta = self.rng.normal(scale=0.1, size=self.D) if theta is None else np.array(theta, dtype=np.float64)
+        self.n_draw = 0
+        self.acceptance_probability = 0
+
+    def _logq(self, a, b):
+        z = (a - b) / self.stepsize
+        return -0.5 * z.dot(z)
+
+    def draw(self):
+        self.n_draw += 1
+        xi = self.rng.normal(size=self.D)
+        cand = self.theta + xi * self.stepsize
+        r = self.model.log_density(cand)
+        r -= self.model.log_density(self.theta)
+        r += self._logq(self.theta, cand)
+        r -= self._logq(cand, self.theta)
+        a = np.log(self.rng.uniform()) < np.minimum(0.0, r)
+        self.theta = a * cand + (1 - a) * self.theta
+        self.acceptance_probability += (a - self.acceptance_probability) / self.n_draw
+        return self.theta
+
+
 class ReplayRNG:
     """Plays back a golden tape's variates through the Generator calls the sampler makes."""
 

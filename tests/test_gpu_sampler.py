@@ -297,6 +297,53 @@ def test_sub_klhr_sinh_class():
     assert 0.85 < s.acceptance_probability < 1.0
 
 
+def test_mh_sampler_against_numpy_replay_and_reference_rate():
+    """reference mh.py: the kernel emits xi and u; a NumPy replay of mh.py:21-30 gives the same chain; the
+    acceptance rate at the reference's stepsize matches its seeded run (tests/golden freerun_*_mh)."""
+    import json
+    from conftest import GOLDEN
+    for name in ("freerun_normal_d2_mh", "freerun_funnel_d2_mh"):
+        t = dict(np.load(GOLDEN / f"{name}.npz"))
+        meta, data = json.loads(str(t["meta_json"])), json.loads(str(t["data_json"]))
+        step = meta["ctor"]["stepsize"]
+        model = kb.BSModel(stan_file=f"stan/{meta['model']}.stan", data=data, device=device())
+        om = stan_models.make_model(meta["model"], data)
+        B, S = 2000, 5
+        s = kb.MH(model, step, seed=3, chains=B)
+        theta = s.theta.cpu().numpy().copy()
+        tr = kb.Trace(S, B, model.dim(), 2, torch.float64, device(), variates=True, rho=True)
+        s._advance(S, trace=tr)
+        torch.cuda.synchronize()
+        for k in range(S):
+            xi, u = tr.rho[k].cpu().numpy(), tr.u[k].cpu().numpy()
+            cand = theta + xi * step
+            r = om.lp(cand) - om.lp(theta)
+            acc = np.log(u) < np.minimum(0.0, r)
+            assert np.array_equal(acc, tr.accept[k].cpu().numpy().astype(bool))
+            theta = np.where(acc[:, None], cand, theta)
+        assert np.allclose(s.theta.cpu().numpy(), theta, rtol=1e-13, atol=1e-13)
+        xi = tr.rho.cpu().numpy().ravel()
+        assert abs(xi.mean()) < 5 / np.sqrt(xi.size) and abs(xi.var() - 1) < 0.02
+        # stationary acceptance: start many chains from the reference chain's own states
+        starts = t["thetas"][1000::1][:2000]
+        s2 = kb.MH(model, step, seed=4, theta=starts, chains=len(starts))
+        s2.run(200)
+        acc_ref = (np.abs(np.diff(t["thetas"][1000:], axis=0)).sum(1) > 0).astype(float)
+        nb = 20
+        bm = acc_ref[:(len(acc_ref) // nb) * nb].reshape(nb, -1).mean(1)
+        se = bm.std(ddof=1) / np.sqrt(nb)
+        assert abs(s2.acceptance_probability - acc_ref.mean()) <= 4 * se + 0.01, (s2.acceptance_probability, acc_ref.mean(), se)
+    # posterior: normal D = 10, unit variances
+    model = kb.BSModel(stan_file="stan/normal.stan", data={"D": 10}, device=device())
+    m = kb.MH(model, 0.7, seed=5, chains=4096)
+    m.run(2000)
+    s1, s2_ = m.run(3000, chain_stats=True)
+    summ = chain_summary(s1, s2_, 3000)
+    assert float((summ["mean"].abs() / summ["mcse_mean"]).max()) < 4.5
+    assert float(((summ["var"] - 1).abs() / summ["mcse_var"]).max()) < 4.5
+    assert m.sample(7).shape == (7, 4096, 10)
+
+
 def test_checkpoint_resume_is_bit_exact(tmp_path):
     """run(a) ; save ; load into a fresh sampler ; run(b)  ==  run(a + b), across a window closure and for
     both the accumulating and the fast kernels (counter-based RNG: no generator state to save)."""

@@ -53,6 +53,19 @@ def test_port_reproduces_seeded_free_runs_of_the_reference(name):
     assert s.grad_evals == int(t["grad_evals"])
 
 
+@pytest.mark.parametrize("name", ["freerun_normal_d2_mh", "freerun_funnel_d2_mh"])
+def test_mh_port_reproduces_reference(name):
+    import json
+    from conftest import GOLDEN
+    from oracle.ref_port import MHChain
+    t = dict(np.load(GOLDEN / f"{name}.npz"))
+    meta, data = json.loads(str(t["meta_json"])), json.loads(str(t["data_json"]))
+    s = MHChain(BSModel(stan_file=meta["model"] + ".stan", data=data), meta["ctor"]["stepsize"], seed=meta["ctor"]["seed"])
+    out = np.array([s.draw() for _ in range(meta["draws"])])
+    assert np.array_equal(out, t["thetas"])
+    assert float(np.ravel(s.acceptance_probability)[0]) == float(t["acceptance_probability"])
+
+
 def test_quadrature_table(tapes):
     # values after the reference's normalisation, klhr.py:46-49
     from oracle.ref_port import gauss_hermite_probabilists
