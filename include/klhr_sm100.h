@@ -49,7 +49,8 @@ typedef struct klhr_model {
     int32_t dim;         /* number of unconstrained parameters         */
     int32_t i0, i1;      /* model integers, see enum                   */
     double s0, s1;       /* model scalars, see enum                    */
-    const void* data0;   /* device buffer of `dtype` reals, see enum   */
+    const void* data0;   /* device buffer, see enum: `dtype` reals, except the sufficient statistics
+                            of arK and earnings which are ALWAYS fp64   */
     const void* data1;   /* reserved                                   */
 } klhr_model_t;
 

@@ -108,7 +108,9 @@ class BSModel:
             h = self._host
             buf = None
             if h["data0"] is not None:
-                buf = torch.as_tensor(h["data0"], dtype=torch.float64).to(device=device, dtype=dtype).contiguous()
+                # sufficient statistics (arK, earnings) stay fp64 whatever the arithmetic type (klhr_models.cuh)
+                bt = torch.float64 if self.name in ("arK", "earnings") else dtype
+                buf = torch.as_tensor(h["data0"], dtype=torch.float64).to(device=device, dtype=bt).contiguous()
             desc = _lib.ModelDesc(id=_lib.MODEL_IDS[self.name], dim=h["dim"], i0=h["i0"], i1=h["i1"],
                                   s0=h["s0"], s1=h["s1"],
                                   data0=buf.data_ptr() if buf is not None else None, data1=None)

@@ -257,35 +257,39 @@ struct ARK {
     __device__ static __forceinline__ void gram_forms(const R* th, const R* rh, int lane, unsigned m,
                                                       const ModelParams& mp, R& q0, R& q1, R& q2,
                                                       R& p0, R& p1, R& p2, R* gphi /*(G phi - c)_lane or null*/) {
+        // The sufficient statistics are ALWAYS fp64 (whatever R is) and the forms are accumulated in
+        // fp64: sum r^2 = yy - 2 phi.c + phi^T G phi cancels to a few per cent of its terms, which fp32
+        // storage cannot carry (D = K + 2 is tiny, so this costs nothing).
         const int K1 = mp.i0 + 1;
-        const R* G = reinterpret_cast<const R*>(mp.p0);
-        const R* cv = G + K1 * K1;
-        const R yy = __ldg(cv + K1);
-        R s_pc = 0, s_pGp = 0, s_rGp = 0, s_rGr = 0, s_rc = 0, pp = 0, pr = 0, rr = 0;
+        const double* G = reinterpret_cast<const double*>(mp.p0);
+        const double* cv = G + K1 * K1;
+        const double yy = __ldg(cv + K1);
+        double s_pc = 0, s_pGp = 0, s_rGp = 0, s_rGr = 0, s_rc = 0;
+        R pp = 0, pr = 0, rr = 0;
         for (int i = lane; i < K1; i += kOct) {
-            R Gp = 0, Gr = 0;
+            double Gp = 0, Gr = 0;
             for (int k = 0; k < K1; ++k) {
-                const R gik = __ldg(G + i * K1 + k);
-                Gp += gik * th[k];
-                Gr += gik * rh[k];
+                const double gik = __ldg(G + i * K1 + k);
+                Gp += gik * (double)th[k];
+                Gr += gik * (double)rh[k];
             }
-            const R ci = __ldg(cv + i);
-            s_pc += th[i] * ci;
-            s_pGp += th[i] * Gp;
-            s_rGp += rh[i] * Gp;
-            s_rGr += rh[i] * Gr;
-            s_rc += rh[i] * ci;
+            const double ci = __ldg(cv + i);
+            s_pc += (double)th[i] * ci;
+            s_pGp += (double)th[i] * Gp;
+            s_rGp += (double)rh[i] * Gp;
+            s_rGr += (double)rh[i] * Gr;
+            s_rc += (double)rh[i] * ci;
             pp += th[i] * th[i];
             pr += th[i] * rh[i];
             rr += rh[i] * rh[i];
-            if (gphi) gphi[i] = Gp - ci;
+            if (gphi) gphi[i] = (R)(Gp - ci);
         }
         s_pc = oct_sum(s_pc, m); s_pGp = oct_sum(s_pGp, m); s_rGp = oct_sum(s_rGp, m);
         s_rGr = oct_sum(s_rGr, m); s_rc = oct_sum(s_rc, m);
         p0 = oct_sum(pp, m); p1 = oct_sum(pr, m); p2 = oct_sum(rr, m);
-        q0 = yy - R(2) * s_pc + s_pGp;          // sum r^2 at phi
-        q1 = s_rGp - s_rc;                      // 1/2 d/dy sum r^2
-        q2 = s_rGr;
+        q0 = (R)(yy - 2.0 * s_pc + s_pGp);      // sum r^2 at phi
+        q1 = (R)(s_rGp - s_rc);                 // 1/2 d/dy sum r^2
+        q2 = (R)s_rGr;
     }
     __device__ static __forceinline__ R value(const Coef& c, R y) {
         const R u = c.u0 + y * c.ru;
@@ -339,9 +343,9 @@ template <typename R>
 struct Earnings {
     static constexpr bool kDenseCta = false;
     struct Coef { R b1, b2, r1, r2, us0, rs, ut0, rt, S0, S1, S2, nm1, l0; };
-    struct Stats { R N, Se, Sh, See, Seh, Shh; };
+    struct Stats { double N, Se, Sh, See, Seh, Shh; };        // always fp64 (dollar-scale sums)
     __device__ static __forceinline__ Stats stats(const ModelParams& mp) {
-        const R* p = reinterpret_cast<const R*>(mp.p0);
+        const double* p = reinterpret_cast<const double*>(mp.p0);
         Stats s;
         s.N = __ldg(p); s.Se = __ldg(p + 1); s.Sh = __ldg(p + 2);
         s.See = __ldg(p + 3); s.Seh = __ldg(p + 4); s.Shh = __ldg(p + 5);
@@ -362,14 +366,14 @@ struct Earnings {
         Coef c;
         c.b1 = th[0]; c.b2 = th[1]; c.us0 = th[2]; c.ut0 = th[3];
         c.r1 = rh[0]; c.r2 = rh[1]; c.rs = rh[2]; c.rt = rh[3];
-        c.S0 = s.See - R(2) * c.b1 * s.Se - R(2) * c.b2 * s.Seh + c.b1 * c.b1 * s.N + R(2) * c.b1 * c.b2 * s.Sh
-               + c.b2 * c.b2 * s.Shh;
+        const double b1 = c.b1, b2 = c.b2, r1 = c.r1, r2 = c.r2;
+        c.S0 = (R)(s.See - 2.0 * b1 * s.Se - 2.0 * b2 * s.Seh + b1 * b1 * s.N + 2.0 * b1 * b2 * s.Sh + b2 * b2 * s.Shh);
         // X^T r with r = e - b1 - b2 h
-        const R xr1 = s.Se - c.b1 * s.N - c.b2 * s.Sh;
-        const R xr2 = s.Seh - c.b1 * s.Sh - c.b2 * s.Shh;
-        c.S1 = -(c.r1 * xr1 + c.r2 * xr2);
-        c.S2 = c.r1 * c.r1 * s.N + R(2) * c.r1 * c.r2 * s.Sh + c.r2 * c.r2 * s.Shh;
-        c.nm1 = s.N - R(1);
+        const double xr1 = s.Se - b1 * s.N - b2 * s.Sh;
+        const double xr2 = s.Seh - b1 * s.Sh - b2 * s.Shh;
+        c.S1 = (R)(-(r1 * xr1 + r2 * xr2));
+        c.S2 = (R)(r1 * r1 * s.N + 2.0 * r1 * r2 * s.Sh + r2 * r2 * s.Shh);
+        c.nm1 = (R)(s.N - 1.0);
         c.l0 = 0;
         c.l0 = value(c, R(0));
         return c;
@@ -403,15 +407,17 @@ struct Earnings {
         const Stats s = stats(mp);
         const R b1 = th[0], b2 = th[1], us = th[2], ut = th[3];
         const R et = r_exp(ut), em2t = r_exp(-R(2) * ut), es = r_exp(us), em2 = r_exp(-R(2) * us);
-        const R ssr = s.See - R(2) * b1 * s.Se - R(2) * b2 * s.Seh + b1 * b1 * s.N + R(2) * b1 * b2 * s.Sh + b2 * b2 * s.Shh;
+        const double d1 = b1, d2 = b2;
+        const R ssr = (R)(s.See - 2.0 * d1 * s.Se - 2.0 * d2 * s.Seh + d1 * d1 * s.N + 2.0 * d1 * d2 * s.Sh + d2 * d2 * s.Shh);
         const R q1 = b1 * b1 * em2t, q2 = b2 * b2 * em2t;
+        const R nN = (R)s.N;
         if (g && lane == 0) {
-            g[0] = -R(6) * b1 * em2t / (R(5) + q1) + em2 * (s.Se - b1 * s.N - b2 * s.Sh);
-            g[1] = -R(6) * b2 * em2t / (R(5) + q2) + em2 * (s.Seh - b1 * s.Sh - b2 * s.Shh);
-            g[2] = -R(0.1) * es + R(1) - s.N + em2 * ssr;
+            g[0] = -R(6) * b1 * em2t / (R(5) + q1) + em2 * (R)(s.Se - d1 * s.N - d2 * s.Sh);
+            g[1] = -R(6) * b2 * em2t / (R(5) + q2) + em2 * (R)(s.Seh - d1 * s.Sh - d2 * s.Shh);
+            g[2] = -R(0.1) * es + R(1) - nN + em2 * ssr;
             g[3] = -R(0.01) * et - R(1) + R(6) * q1 / (R(5) + q1) + R(6) * q2 / (R(5) + q2);
         }
-        return -R(0.01) * et - ut - R(3) * (r_log1p(q1 / R(5)) + r_log1p(q2 / R(5))) - R(0.1) * es + us - s.N * us
+        return -R(0.01) * et - ut - R(3) * (r_log1p(q1 / R(5)) + r_log1p(q2 / R(5))) - R(0.1) * es + us - nN * us
                - R(0.5) * em2 * ssr;
     }
 };

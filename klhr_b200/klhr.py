@@ -243,7 +243,9 @@ class KLHR(MCMCBase):
         if self._family == "sinh":
             init4 = torch.as_tensor(self.rng.normal(size=(B, 4))).to(self.device, self.dtype).contiguous()
         scratch = self._theta.clone()
-        tr = engine.step_replay(self.model, self._fit, scratch, rho_t, z, zeros, half, init4=init4)
+        import dataclasses
+        fit_only = dataclasses.replace(self._fit, overrelax_K=0)      # the proposal is irrelevant to the fit
+        tr = engine.step_replay(self.model, fit_only, scratch, rho_t, z, zeros, half, init4=init4)
         eta = tr.eta[0]
         return eta[0].double().cpu().numpy() if self.chains == 1 else eta
 

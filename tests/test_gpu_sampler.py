@@ -278,6 +278,7 @@ def test_sampler_api_matches_reference_surface():
     d = b.sample(10, thin=3)
     assert d.shape == (10, 64, 2) and b._draw == 27 and torch.equal(d[-1], b.theta)
     assert kb.KLHRSINH(model)._fit.overrelax_K == 10 and kb.KLHR(model)._fit.overrelax_K == 0   # reference defaults
+    assert kb.KLHRSINH(model, seed=2).fit(np.array([0.6, 0.8])).shape == (4,)
     with pytest.raises(NotImplementedError):
         kb.BSModel(stan_file="stan/garch.stan", data={})      # not among the implemented targets
 
