@@ -39,7 +39,7 @@ class KLHR(MCMCBase):
                  windowsize=50, windowscale=2, tol=1e-12, grad_clip=1e15, scale_clip=600,
                  scale_dir_cov=False, overrelaxed=False, eigen_method_one=True, max_init_tries=100, *,
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
-                 pca_stride=10, fit_budget=None):
+                 pca_stride=10, moments_every_draw=False, fit_budget=None):
         super().__init__(bsmodel, -1, theta=theta, seed=seed, chains=chains, dtype=dtype, device=device)
         if not 1 <= int(K) <= 50:
             raise ValueError("K must be in 1..50 (the reference clips it there, klhr.py:213)")
@@ -61,6 +61,10 @@ class KLHR(MCMCBase):
         self._overrelaxed = overrelaxed
         self._eigen_method_one = eigen_method_one
         self._pca_stride = max(1, int(pca_stride))
+        # False (default): the window moments come from the same ensemble snapshots as the PCA sums
+        # (every pca_stride draws, all chains) and the warm-up runs on the fast kernels; True: every
+        # non-closure draw of every chain is accumulated in-kernel like klhr.py:216-218 does per draw
+        self._moments_every_draw = bool(moments_every_draw)
         self._group = process_group
         dev = self.device
         self._onlinemoments = OnlineMoments(self.D, device=dev)
@@ -144,7 +148,7 @@ class KLHR(MCMCBase):
                 steps = min(steps, nxt - self._draw, self._pca_stride)
                 closes = self._draw + steps == nxt
             kw = {}
-            if adapting:
+            if adapting and self._moments_every_draw:
                 mom = self._onlinemoments
                 kw.update(shift=self._shift_dev, pooled_s1=mom.s1, pooled_s2=mom.s2, skip_accum_last=closes)
             elif chain_s1 is not None:
@@ -163,7 +167,8 @@ class KLHR(MCMCBase):
             self._draw += steps
             done += steps
             if adapting:
-                self._onlinemoments.add_sums(self.chains * (steps - (1 if closes else 0)))
+                if self._moments_every_draw:
+                    self._onlinemoments.add_sums(self.chains * (steps - (1 if closes else 0)))
                 if closes:
                     self._close_window()
                 else:
@@ -172,8 +177,12 @@ class KLHR(MCMCBase):
     def _snapshot_update(self):
         """Pooled analogue of klhr.py:216-219 on the current ensemble: PCA second moments of
         (theta - _mean) and, for ``scale_dir_cov``, gradient moments."""
-        pca = self._onlinepca
-        engine.outer_accumulate(self._theta, self._shift_dev, pca.outer)
+        pca, mom = self._onlinepca, self._onlinemoments
+        if self._moments_every_draw:
+            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer)
+        else:       # first moments ride along; second moments are the diagonal of the outer-product sum
+            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, mom.s1)
+            mom.N += self.chains
         pca.add_sums(self.chains)
         if self._scale_dir_cov:
             _, g = self.model.log_density_gradient(self._theta)
@@ -182,6 +191,8 @@ class KLHR(MCMCBase):
     def _close_window(self):
         """klhr.py:202-214 with pooled sums; identical result on every rank."""
         mom, gmom, pca = self._onlinemoments, self._onlinemoments_density, self._onlinepca
+        if not self._moments_every_draw:
+            mom.s2.copy_(torch.diagonal(pca.outer))
         allreduce_adaptation([mom, gmom], pca, group=self._group)
         self._mean = mom.mean().cpu().numpy()
         self._cov = mom.var().cpu().numpy()

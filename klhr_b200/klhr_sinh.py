@@ -22,7 +22,7 @@ class KLHRSINH(KLHR):
                  windowsize=50, windowscale=2, tol=1e-10, grad_clip=1e15, scale_clip=300,
                  scale_dir_cov=False, overrelaxed=True, eigen_method_one=False, max_init_tries=100, *,
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
-                 pca_stride=10, fit_budget=None):
+                 pca_stride=10, moments_every_draw=False, fit_budget=None):
         if dtype != torch.float64:
             raise TypeError("the sinh-arcsinh family needs float64 (sinh/cosh of up to +-300, "
                             "klhr_sinh.py:100-110)")
@@ -32,6 +32,7 @@ class KLHRSINH(KLHR):
                          overrelaxed=overrelaxed, eigen_method_one=eigen_method_one,
                          max_init_tries=max_init_tries, chains=chains, dtype=dtype, device=device,
                          process_group=process_group, chain_offset=chain_offset, pca_stride=pca_stride,
+                         moments_every_draw=moments_every_draw,
                          fit_budget=fit_budget)
 
     def _clip_J(self, J):
