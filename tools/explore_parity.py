@@ -1,7 +1,7 @@
 """Exploration (not a test): error statistics of the CUDA replay step vs the oracle."""
 import glob, os, sys, time
 import numpy as np, torch
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from conftest import load_tape
