@@ -10,6 +10,8 @@ from gpu_util import replay_both, rel_errors
 for path in sorted(glob.glob("tests/golden/*.npz")):
     name = os.path.basename(path)[:-4]
     t, meta, data = load_tape(name)
+    if "rho" not in t:          # stats_* / freerun_* tapes hold no per-draw inputs
+        continue
     for dtype in (torch.float64, torch.float32):
         t0 = time.time()
         gpu, ref = replay_both(meta["model"], data, meta["family"], t["theta0"], t["rho"], t["z_init"],
