@@ -17,7 +17,7 @@
 namespace klhr {
 
 #ifndef KLHR_CHAIN_MINCTAS
-#define KLHR_CHAIN_MINCTAS 8
+#define KLHR_CHAIN_MINCTAS 16   // 128 registers: the extra resident warps beat the small spills (measured, funnel)
 #endif
 
 template <typename R, typename Model, int NE, bool kReplay>
