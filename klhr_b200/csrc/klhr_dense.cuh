@@ -37,18 +37,53 @@ __device__ inline void dense_cta_quadratic(const double* th_tile, const double* 
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-        for (int k0 = 0; k0 < D; k0 += 4) {
-            const int k = k0 + k4;
-            const bool kin = k < D;
-            const double a0 = (kin && r8 < cpb) ? rh_tile[(size_t)r8 * Dpad + k] : 0.0;
-            const double a1 = (kin && 8 + r8 < cpb) ? rh_tile[(size_t)(8 + r8) * Dpad + k] : 0.0;
+        // Fast path (every column tile of the chunk is full and D % 4 == 0): no bounds predicates, one
+        // base pointer per tile, and the 8 B fragments of step k0 + 4 are loaded while the 16 DMMAs of
+        // step k0 run (register double buffer) so the L2 latency of P hides behind the tensor pipe.
+        const int nt_last = (chunk * 8 + 7) * n_warps + warp;
+        if ((D & 3) == 0 && (nt_last + 1) * 8 <= D) {
+            const double* pb0[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int nt = (chunk * 8 + q) * n_warps + warp;
-                const int n = nt * 8 + r8;             // B fragment: row k4, column r8 of the tile
-                const double b = (kin && n < D) ? __ldg(P + (size_t)k * D + n) : 0.0;
-                dmma_m8n8k4(acc[0][q][0], acc[0][q][1], a0, b);
-                dmma_m8n8k4(acc[1][q][0], acc[1][q][1], a1, b);
+            for (int q = 0; q < 8; ++q)
+                pb0[q] = P + (size_t)k4 * D + ((chunk * 8 + q) * n_warps + warp) * 8 + r8;
+            const double* ra0 = rh_tile + (size_t)r8 * Dpad + k4;
+            const double* ra1 = rh_tile + (size_t)(8 + r8) * Dpad + k4;
+            const bool row0 = r8 < cpb, row1 = 8 + r8 < cpb;
+            double bn[8], an0 = row0 ? ra0[0] : 0.0, an1 = row1 ? ra1[0] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bn[q] = __ldg(pb0[q]);
+            for (int k0 = 0; k0 < D; k0 += 4) {
+                double bc[8];
+                const double a0 = an0, a1 = an1;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) bc[q] = bn[q];
+                if (k0 + 4 < D) {
+                    const size_t off = (size_t)(k0 + 4) * D;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bn[q] = __ldg(pb0[q] + off);
+                    an0 = row0 ? ra0[k0 + 4] : 0.0;
+                    an1 = row1 ? ra1[k0 + 4] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    dmma_m8n8k4(acc[0][q][0], acc[0][q][1], a0, bc[q]);
+                    dmma_m8n8k4(acc[1][q][0], acc[1][q][1], a1, bc[q]);
+                }
+            }
+        } else {
+            for (int k0 = 0; k0 < D; k0 += 4) {
+                const int k = k0 + k4;
+                const bool kin = k < D;
+                const double a0 = (kin && r8 < cpb) ? rh_tile[(size_t)r8 * Dpad + k] : 0.0;
+                const double a1 = (kin && 8 + r8 < cpb) ? rh_tile[(size_t)(8 + r8) * Dpad + k] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int nt = (chunk * 8 + q) * n_warps + warp;
+                    const int n = nt * 8 + r8;             // B fragment: row k4, column r8 of the tile
+                    const double b = (kin && n < D) ? __ldg(P + (size_t)k * D + n) : 0.0;
+                    dmma_m8n8k4(acc[0][q][0], acc[0][q][1], a0, b);
+                    dmma_m8n8k4(acc[1][q][0], acc[1][q][1], a1, b);
+                }
             }
         }
         // C fragment: row r8, columns 2*k4 + {0,1} of tile nt.  Fold V into rho.V and theta.V.

@@ -33,7 +33,9 @@ def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, dire
     ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 4}, "gauss", True),
     ("funnel", {"D": 1}, "sinh", False), ("funnel", {"D": 1}, "sinh", True),
     ("rosenbrock", {"D": 2}, "gauss", False), ("ar1", {"N": 20}, "gauss", False),
-    ("ar1", {"N": 150}, "gauss", False), ("normal", {"D": 3}, "sinh", False)])
+    ("ar1", {"N": 150}, "gauss", False), ("normal", {"D": 3}, "sinh", False),
+    ("corr-normal", {"N": 256, "rho": 0.9}, "gauss", False),      # DMMA fast path (klhr_dense.cuh)
+    ("corr-normal", {"N": 44, "rho": 0.5}, "gauss", True)])       # DMMA generic path, ragged tiles
 def test_free_running_step_equals_oracle_on_emitted_variates(model_name, data, family, force_octet):
     """The free-running kernel emits the direction and variates it drew; replaying them through
     the oracle must give the same fit, proposal, ratio, flag and state (fp64, 1e-10)."""
