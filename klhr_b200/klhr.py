@@ -260,6 +260,14 @@ class KLHR(MCMCBase):
         eta = tr.eta[0]
         return eta[0].double().cpu().numpy() if self.chains == 1 else eta
 
+    def swap_state(self, theta):
+        """Use ``theta`` (B, D) -- a contiguous device tensor of the sampler's dtype -- as the live chain
+        state WITHOUT copying, e.g. to double-buffer host transfers against ``run``."""
+        if tuple(theta.shape) != (self.chains, self.D) or theta.dtype != self.dtype or not theta.is_cuda \
+                or not theta.is_contiguous():
+            raise ValueError("swap_state needs a contiguous (chains, D) CUDA tensor of the sampler's dtype")
+        self._theta = theta
+
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
         """Everything needed to continue the run bit for bit: the RNG is counter based (a function of
