@@ -143,14 +143,15 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
             const float* mcol_s = s_mean + (size_t)(has_mean ? col : 0) * D;
             const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
             const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
-            const bool pend = cp != R(0);
+            const bool pend_rt = cp != R(0);
             R ss = 0, sA = 0, sB = 0;
             // Element i = g0 + j + 8 s, slot s = 4 t + r of this lane  <->  Philox counter slot
             // kSlotDir + j + 8 t + g0 / 4, word r.  A half handles slots 8h..8h+7 (blocks 2h, 2h+1).  When
             // the half is FULL (every slot live for every lane) the body carries no predicates at all;
             // only the last, partial half pays for bounds checks and skips its dead slots.
-            auto do_half = [&](auto full_tag, const int g0, const int h) {
+            auto do_half = [&](auto full_tag, auto pend_tag, const int g0, const int h) {
                 constexpr bool kFull = decltype(full_tag)::value;
+                constexpr bool pend = decltype(pend_tag)::value;   // a move of the previous draw is pending
                 // 1. issue the long-latency loads first (theta slice from L2, previous x); they hide
                 //    behind the RNG arithmetic of step 2.  Weights, scales and means are read from
                 //    shared memory at the point of use (preloading them needs > 128 registers).
@@ -212,8 +213,14 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     if (g0 + 64 * h >= D) break;          // warp-uniform: nothing left
-                    if (g0 + 64 * h + 63 < D) do_half(std::true_type{}, g0, h);
-                    else do_half(std::false_type{}, g0, h);
+                    const bool full = g0 + 64 * h + 63 < D;
+                    if (pend_rt) {
+                        if (full) do_half(std::true_type{}, std::true_type{}, g0, h);
+                        else do_half(std::false_type{}, std::true_type{}, g0, h);
+                    } else {
+                        if (full) do_half(std::true_type{}, std::false_type{}, g0, h);
+                        else do_half(std::false_type{}, std::false_type{}, g0, h);
+                    }
                 }
             }
             if (last) continue;
@@ -323,7 +330,10 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
                   (size_t)(a.mp.D + n_cols) * sizeof(float);
     // budget per CTA so that all tiles of B = 65 536 are resident at once: 14 CTAs per SM with
     // 32-chain tiles, 28 with 16-chain tiles; minus the 1 KB the driver reserves per CTA
-    const size_t budget = 228 * 1024 / (kTilePasses == 8 ? 14 : 28) - 1024;
+#ifndef KLHR_TILE_SMEM_CTAS
+#define KLHR_TILE_SMEM_CTAS (kTilePasses == 8 ? 14 : 28)
+#endif
+    const size_t budget = 228 * 1024 / (KLHR_TILE_SMEM_CTAS) - 1024;
     const size_t mean_bytes = (size_t)n_stored * a.mp.D * sizeof(float);
     (void)budget;
     a.tile_mean_smem = n_stored > 0 ? 1 : 0;
