@@ -1,10 +1,11 @@
 // klhr_b200 -- device-side building blocks shared by all kernels (sm_100a).
 //
-// Execution shape: an OCTET (8 consecutive lanes of a warp) owns one chain.  The 8 lanes
-// are the 8 Gauss-Hermite nodes during the KL fit (reference klhr.py:110-117 loops over
-// them serially), the 8 back-tracking candidates during the 1-D mode search, and 8
-// interleaved slices of the D-vector during direction / line-setup / update.  Reductions
-// are 3-level xor-shuffles confined to the octet.
+// Execution shapes.  An OCTET (8 consecutive lanes of a warp) cooperates on one chain for
+// everything that walks the D-vector (direction, line setup, update): 8 interleaved slices,
+// 3-level xor-shuffle reductions confined to the octet.  The line fit runs either on the same
+// octet (klhr_step.cuh: the 8 lanes are the 8 Gauss-Hermite nodes of klhr.py:110-117 and the 8
+// back-tracking candidates of the mode search) or thread-per-chain (klhr_tile.cuh,
+// klhr_chain.cuh: a warp owns 32 chains, lane 8o+j fits the chain octet o handled in pass j).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -27,13 +27,6 @@ struct FitParams {
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
 };
 
-template <typename R>
-struct FitResult {
-    R eta[4];
-    int evals;             // line evaluations executed (the reference's grad_evals, klhr.py:132,140)
-    bool converged;
-};
-
 template <int G, typename R>
 __device__ __forceinline__ R grp_sum(R v, unsigned m) {
     if constexpr (G == kOct) return oct_sum(v, m);

@@ -29,7 +29,6 @@ struct StepArgs {
     void* theta;
     long long B;
     int Dpad;
-    int tile_mean_smem;      // tile kernel: direction-mean columns staged in shared memory
     // replay inputs
     const void* rho;
     const void* z_init;

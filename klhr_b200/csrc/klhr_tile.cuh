@@ -22,7 +22,11 @@
 
 namespace klhr {
 
-// chains per octet per draw (passes of the D-phase); a warp owns 4 * kTilePasses chains
+// Tuning knobs (measured on B200, ill-normal D = 100, 65 536 chains):
+//   KLHR_TILE_PASSES  chains per octet per draw; a warp owns 4 * passes chains.  8 (32-chain tiles, 13.8
+//                     one-warp CTAs per SM) beat 6 and 4: smaller tiles need <= 96 / 72 registers and spill.
+//   KLHR_TILE_MINCTAS 16 -> at most 128 registers, so that 14 tiles per SM are resident in ONE wave.
+//   KLHR_TILE_W_SMEM  per-coordinate weights staged in shared memory (1) or read through L1 (0).
 #ifndef KLHR_TILE_PASSES
 #define KLHR_TILE_PASSES 8
 #endif
@@ -68,10 +72,10 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
     const int L = threadIdx.x;
     const int o = L >> 3, j = L & 7;
     const unsigned om = oct_mask();
-    // shared memory: w[D] (R) | xs[32][Dx] (XT) | sd[D] (float) | cdf[n_cols] (float) | mean[n_sm][D] (float).
-    // Every byte counts: 14 one-warp CTAs must fit per SM for the 2048 tiles of B = 65 536 to be
-    // resident in one wave, so the stored direction-mean columns go to shared memory only when
-    // they fit that budget (n_sm = a.tile_mean_smem columns), otherwise they are read from global.
+    // shared memory: w[D] (R) | xs[32][Dx] (XT) | sd[D] (float) | cdf[n_cols] (float) | mean[n_stored][D] (float).
+    // Every byte counts: 14 one-warp CTAs must fit per SM (<= 15.6 KB each) for the 2048 tiles of
+    // B = 65 536 to be resident in one wave; the dispatcher (klhr_api.cu:tile_applies) therefore sends
+    // direction laws with more than two stored mean columns to the octet kernel.
     R* s_w = reinterpret_cast<R*>(smem_raw);
     XT* xs = reinterpret_cast<XT*>(s_w + (KLHR_TILE_W_SMEM ? ((D + 1) & ~1) : 0));
     float* s_sd = reinterpret_cast<float*>(xs + (size_t)kTileChains * Dx);
@@ -328,16 +332,7 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     size_t smem = (KLHR_TILE_W_SMEM ? (size_t)((a.mp.D + 1) & ~1) * sizeof(R) : 0) + (size_t)kTileChains * a.Dpad * xbytes +
                   (size_t)(a.mp.D + n_cols) * sizeof(float);
-    // budget per CTA so that all tiles of B = 65 536 are resident at once: 14 CTAs per SM with
-    // 32-chain tiles, 28 with 16-chain tiles; minus the 1 KB the driver reserves per CTA
-#ifndef KLHR_TILE_SMEM_CTAS
-#define KLHR_TILE_SMEM_CTAS (kTilePasses == 8 ? 14 : 28)
-#endif
-    const size_t budget = 228 * 1024 / (KLHR_TILE_SMEM_CTAS) - 1024;
-    const size_t mean_bytes = (size_t)n_stored * a.mp.D * sizeof(float);
-    (void)budget;
-    a.tile_mean_smem = n_stored > 0 ? 1 : 0;
-    smem += mean_bytes;
+    smem += (size_t)n_stored * a.mp.D * sizeof(float);
     if (smem > 227 * 1024) return -20;
     const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
                             : (const void*)tile_kernel<R, kScaled, float, false>;
