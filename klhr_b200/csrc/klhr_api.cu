@@ -87,7 +87,10 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
 static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
     // at most 2 stored direction-mean columns: they live in the tile's shared memory (J = 2 default)
     const int n_stored = a.dir.mean_cols ? a.dir.n_cols - a.dir.n_zero_cols : 0;
-    return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && !a.acc.draws &&
+    // the warp's x tile (32 x D fp32) must stay small enough for several one-warp CTAs per SM;
+    // beyond D ~ 250 the octet kernel (theta resident in shared memory, fewer chains per CTA) takes over
+    const bool small = (size_t)kTileChains * pad_dim(a.mp.D, 4) * 4 <= 32 * 1024;
+    return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && !a.acc.draws && small &&
            (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && n_stored <= 2;
 }
 

@@ -106,6 +106,18 @@ def test_other_quadrature_orders(N, force_octet):
         assert np.array_equal(gpu["accept"], ref["accept"])
 
 
+def test_dimension_too_large_is_a_clear_error():
+    """theta and rho rows are staged in shared memory; a dimension that cannot fit is refused with a
+    message, not a crash (and there is no CPU fallback to hide it)."""
+    import klhr_b200 as kb
+    from gpu_util import up, device
+    D = 20_000
+    model = kb.BSModel(stan_file="stan/normal.stan", data={"D": D}, device=device())
+    th = up(np.zeros((8, D)))
+    with pytest.raises(kb._lib.KLHRLibraryError, match="dimension too large"):
+        kb.run(model, kb.FitConfig(), th, 1, 1)
+
+
 def test_empty_and_ragged_batches():
     import klhr_b200 as kb
     from gpu_util import up, device

@@ -29,7 +29,8 @@ def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, dire
 
 @pytest.mark.parametrize("model_name,data,family,force_octet", [
     ("ill-normal", {"D": 100}, "gauss", False), ("ill-normal", {"D": 100}, "gauss", True),
-    ("normal", {"D": 300}, "gauss", False), ("normal", {"D": 5}, "gauss", False),
+    ("normal", {"D": 240}, "gauss", False), ("normal", {"D": 5}, "gauss", False),
+    ("ill-normal", {"D": 1500}, "gauss", False),                  # large D: octet kernel, 64-thread CTAs
     ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 4}, "gauss", True),
     ("funnel", {"D": 1}, "sinh", False), ("funnel", {"D": 1}, "sinh", True),
     ("rosenbrock", {"D": 2}, "gauss", False), ("ar1", {"N": 20}, "gauss", False),
