@@ -19,9 +19,13 @@
 namespace klhr {
 
 constexpr int kThreadsMax = 256;
+// resident 256-thread CTAs per SM the register budget aims for: 3 (<= 80 registers) measured +7..10% over 2
+// on ar1 / ill-normal / funnel; the dense DMMA path keeps 64 accumulator registers and needs 128
 #ifndef KLHR_MIN_CTAS
-#define KLHR_MIN_CTAS 2
+#define KLHR_MIN_CTAS 3
 #endif
+template <typename R, typename Model>
+constexpr int step_min_ctas() { return (Model::kDenseCta && sizeof(R) == 8) ? 2 : KLHR_MIN_CTAS; }
 
 struct StepArgs {
     ModelParams mp;
@@ -58,7 +62,7 @@ __host__ __device__ inline int pad_dim(int D, int real_bytes) {
 }
 
 template <typename R, typename Model, int NE, bool kReplay, bool kAccum>
-__global__ void __launch_bounds__(kThreadsMax, KLHR_MIN_CTAS) step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreadsMax, step_min_ctas<R, Model>()) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.mp.D;
     const int Dpad = a.Dpad;
