@@ -175,7 +175,13 @@ int klhr_mh_run(const klhr_model_t* model, int dtype, void* theta_dev, double st
  * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,
  * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype. */
 int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_dev, double* outer_dev,
-                          double* s1_dev, int64_t n_chains, int32_t dim, void* stream);
+                          double* s1_dev, int64_t n_chains, int32_t dim, double* scratch_dev,
+                          int64_t scratch_doubles, void* stream);
+
+/* Size (in doubles) of the scratch buffer that makes klhr_outer_accumulate DETERMINISTIC: with it the chain
+ * slices write partial planes that are added in a fixed order; with scratch_dev == NULL they are combined
+ * with fp64 atomics (same value up to summation order). */
+int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim);
 
 /* Occupancy query used by bench.py: threads per CTA and dynamic shared bytes the step
  * kernel would be launched with for this problem; returns resident CTAs per SM (<=0 error). */

@@ -6,9 +6,10 @@ CUDA kernels behind the C ABI of ``libklhr_sm100.so`` (include/klhr_sm100.h); th
 CPU fallback.
 """
 from .bsmodel import BSModel
-from .engine import FitConfig, Direction, Trace, step_replay, run, outer_accumulate, launch_info, gauss_hermite
+from .engine import (FitConfig, Direction, Trace, step_replay, run, outer_accumulate, outer_scratch, launch_info,
+                     gauss_hermite)
 
-__all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "outer_accumulate",
+__all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "outer_accumulate", "outer_scratch",
            "launch_info", "gauss_hermite"]
 
 try:  # samplers (import kept soft only so that partial checkouts still expose the engine)

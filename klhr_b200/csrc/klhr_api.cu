@@ -139,7 +139,8 @@ static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, 
 template <typename R>
 __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta, const R* __restrict__ shift,
                                                     double* __restrict__ outer, double* __restrict__ s1,
-                                                    long long B, int D, int chains_per_cta) {
+                                                    long long B, int D, int chains_per_cta,
+                                                    double* __restrict__ scratch) {
     __shared__ double ta[32][33], tb[32][33];
     const int ti = blockIdx.x * 32, tj = blockIdx.y * 32;
     if (tj < ti) return;                                 // upper triangle only; mirrored below
@@ -172,6 +173,21 @@ __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta,
             for (int k = 0; k < 32; ++k) colsum += ta[k][tx];
         __syncthreads();
     }
+    if (scratch) {
+        // deterministic mode: every chain slice writes its partial tile to its own scratch plane
+        // [slice][D*D + D]; outer_reduce_kernel adds the planes in a fixed order
+        double* plane = scratch + (size_t)blockIdx.z * ((size_t)D * D + D);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ti + ty + 8 * q, j = tj + tx;
+            if (i < D && j < D) {
+                plane[(size_t)i * D + j] = acc[q];
+                if (ti != tj) plane[(size_t)j * D + i] = acc[q];
+            }
+        }
+        if (blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) plane[(size_t)D * D + ti + tx] = colsum;
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int i = ti + ty + 8 * q, j = tj + tx;
@@ -181,6 +197,17 @@ __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta,
         }
     }
     if (s1 && blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) atomicAdd(s1 + ti + tx, colsum);
+}
+
+__global__ void outer_reduce_kernel(const double* __restrict__ scratch, double* __restrict__ outer,
+                                    double* __restrict__ s1, int D, int slices) {
+    const size_t plane = (size_t)D * D + D;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane) return;
+    double t = 0;
+    for (int s = 0; s < slices; ++s) t += scratch[(size_t)s * plane + idx];      // fixed order
+    if (idx < (size_t)D * D) outer[idx] += t;
+    else if (s1) s1[idx - (size_t)D * D] += t;
 }
 
 }  // namespace klhr
@@ -342,30 +369,51 @@ int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     return li.ctas_per_sm;
 }
 
+// chain slices of the SYRK: enough to fill the machine (~148 SMs * 4 CTAs over the upper-triangle tiles)
+static void outer_slicing(int64_t n_chains, int32_t dim, int& tiles, long long& slices, long long& per) {
+    tiles = (dim + 31) / 32;
+    const int tri = tiles * (tiles + 1) / 2;
+    slices = (592 + tri - 1) / tri;
+    const long long max_slices = (n_chains + 255) / 256;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    per = (n_chains + slices - 1) / slices;
+    per = ((per + 31) / 32) * 32;
+    slices = (n_chains + per - 1) / per;
+}
+
+int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim) {
+    if (n_chains <= 0 || dim <= 0) return 0;
+    int tiles;
+    long long slices, per;
+    outer_slicing(n_chains, dim, tiles, slices, per);
+    return (int64_t)slices * ((int64_t)dim * dim + dim);
+}
+
 int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_dev, double* outer_dev, double* s1_dev,
-                          int64_t n_chains, int32_t dim, void* stream) {
+                          int64_t n_chains, int32_t dim, double* scratch_dev, int64_t scratch_doubles, void* stream) {
     if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
     if (!theta_dev || !outer_dev) return fail(-1, "theta and outer must not be NULL");
     if (n_chains < 0 || dim <= 0) return fail(-10, "bad sizes");
     if (n_chains == 0) return 0;
-    const int tiles = (dim + 31) / 32;
-    // enough chain slices to fill the machine: ~148 SMs * 4 CTAs over the upper-triangle tiles
-    const int tri = tiles * (tiles + 1) / 2;
-    long long slices = (592 + tri - 1) / tri;
-    const long long max_slices = (n_chains + 255) / 256;
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    long long per = (n_chains + slices - 1) / slices;
-    per = ((per + 31) / 32) * 32;
-    slices = (n_chains + per - 1) / per;
+    int tiles;
+    long long slices, per;
+    outer_slicing(n_chains, dim, tiles, slices, per);
+    if (scratch_dev && scratch_doubles < (int64_t)slices * ((int64_t)dim * dim + dim))
+        return fail(-15, "scratch too small: see klhr_outer_scratch_doubles");
     dim3 grid(tiles, tiles, (unsigned)slices);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == KLHR_F64)
         outer_kernel<double><<<grid, 256, 0, st>>>((const double*)theta_dev, (const double*)shift_dev, outer_dev,
-                                                   s1_dev, n_chains, dim, (int)per);
+                                                   s1_dev, n_chains, dim, (int)per, scratch_dev);
     else
         outer_kernel<float><<<grid, 256, 0, st>>>((const float*)theta_dev, (const float*)shift_dev, outer_dev,
-                                                  s1_dev, n_chains, dim, (int)per);
+                                                  s1_dev, n_chains, dim, (int)per, scratch_dev);
+    if (scratch_dev) {
+        const size_t plane = (size_t)dim * dim + dim;
+        outer_reduce_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(scratch_dev, outer_dev, s1_dev, dim,
+                                                                             (int)slices);
+    }
     return cuda_fail((int)cudaGetLastError(), "klhr_outer_accumulate");
 }
 

@@ -197,15 +197,25 @@ def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Directi
                    "klhr_run")
 
 
-def outer_accumulate(theta, shift, outer, s1=None):
-    """outer (D, D) += sum_c (theta_c - shift)(theta_c - shift)^T ; s1 (D,) += sum_c (theta_c - shift)."""
+def outer_scratch(theta):
+    """Scratch tensor that makes ``outer_accumulate`` deterministic for this (B, D)."""
+    B, D = theta.shape
+    n = int(_lib.load().klhr_outer_scratch_doubles(B, D))
+    return torch.empty(max(n, 1), dtype=torch.float64, device=theta.device)
+
+
+def outer_accumulate(theta, shift, outer, s1=None, scratch=None):
+    """outer (D, D) += sum_c (theta_c - shift)(theta_c - shift)^T ; s1 (D,) += sum_c (theta_c - shift).
+    With ``scratch`` (``outer_scratch(theta)``) the chain slices are combined in a fixed order (bit-reproducible);
+    without it they are combined with fp64 atomics."""
     lib = _lib.load()
     _require_cuda(theta, "theta")
     B, D = theta.shape
     with torch.cuda.device(theta.device):
         st = torch.cuda.current_stream(theta.device).cuda_stream
         _lib.check(lib.klhr_outer_accumulate(_dtype_code(theta.dtype), theta.data_ptr(), _ptr(shift),
-                                             outer.data_ptr(), _ptr(s1), B, D, st),
+                                             outer.data_ptr(), _ptr(s1), B, D, _ptr(scratch),
+                                             scratch.numel() if scratch is not None else 0, st),
                    "klhr_outer_accumulate")
 
 

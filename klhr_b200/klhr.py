@@ -76,6 +76,7 @@ class KLHR(MCMCBase):
         self._eigvecs = np.zeros((self.D, ncol))
         self._eigvals = np.ones(ncol)
         self._draw = 0
+        self._outer_scratch = None
         self._acc_seen = 0.0
         self._accept_count = torch.zeros(self.chains, dtype=torch.int64, device=dev)
         self._evals_total = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -178,10 +179,12 @@ class KLHR(MCMCBase):
         """Pooled analogue of klhr.py:216-219 on the current ensemble: PCA second moments of
         (theta - _mean) and, for ``scale_dir_cov``, gradient moments."""
         pca, mom = self._onlinepca, self._onlinemoments
+        if self._outer_scratch is None:       # fixed-order reduction: seeded runs are bit-reproducible
+            self._outer_scratch = engine.outer_scratch(self._theta)
         if self._moments_every_draw:
-            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer)
+            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, scratch=self._outer_scratch)
         else:       # first moments ride along; second moments are the diagonal of the outer-product sum
-            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, mom.s1)
+            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, mom.s1, scratch=self._outer_scratch)
             mom.N += self.chains
         pca.add_sums(self.chains)
         if self._scale_dir_cov:

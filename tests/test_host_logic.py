@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     if not _lib.LIB_PATH.exists():
         g.build()
     header = (ROOT / "include" / "klhr_sm100.h").read_text()
-    declared = set(re.findall(r"^(?:int|size_t)\s+(klhr_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|size_t|int64_t)\s+(klhr_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.EXPORTS), (declared, set(_lib.EXPORTS))
     lib = _lib.load()
     for name in declared:
