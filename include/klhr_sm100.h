@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KLHR_ABI_VERSION 1
+#define KLHR_ABI_VERSION 2
 
 enum { KLHR_F64 = 0, KLHR_F32 = 1 };
 enum { KLHR_FAMILY_GAUSS = 0, KLHR_FAMILY_SINH = 1 };
@@ -113,7 +113,21 @@ typedef struct klhr_trace {
     void* or_v;       /* [S][B]       over-relaxation: beta variate v (klhr.py:168,171; 1 if unused).
                                       Outputs of klhr_run; INPUTS of klhr_step_replay when
                                       overrelax_K > 0                                            */
+    void* slice_u;    /* [S][B][cap]  slice sampler: uniforms behind the shrinkage proposals, NaN-padded
+                                      (klhr_slice_t.cap columns; output of klhr_slice_run)               */
+    int32_t* slice_n; /* [S][B]       slice sampler: shrinkage proposals consumed (cap + 1: ran out)     */
 } klhr_trace_t;
+
+/* Slice sampling along a random direction (reference Slice.__init__, slice.py:14-39; only m = inf, the
+ * configuration the reference can run: its finite-m branch raises NameError, slice.py:108,124). */
+typedef struct klhr_slice {
+    double w;         /* slice.py:18  width of the stepping-out interval (> 0)                 */
+    double lower;     /* slice.py:20  bounds of the line coordinate (-inf / +inf = none)       */
+    double upper;     /* slice.py:21                                                           */
+    double tol;       /* slice.py:28  rho = x / ||x + tol||                                    */
+    int32_t cap;      /* columns of trace.slice_u / of shrink_u in replay mode (>= 1)          */
+    int32_t reserved;
+} klhr_slice_t;
 
 /* Accumulators of a free-running launch, all optional. */
 typedef struct klhr_accum {
@@ -170,6 +184,23 @@ int klhr_run(const klhr_model_t* model, const klhr_fit_t* fit, const klhr_direct
 int klhr_mh_run(const klhr_model_t* model, int dtype, void* theta_dev, double stepsize, int64_t n_chains,
                 int64_t chain_offset, int64_t draw_offset, int32_t n_steps, uint64_t seed,
                 const klhr_accum_t* accum, const klhr_trace_t* trace, void* stream);
+
+/* Slice sampling along KLHR's adapted directions (reference Slice.draw, slice.py:84-158; an algorithm of
+ * experiment_accuracy.py:56-64) for n_steps draws per chain with the chain's Philox stream.  accum:
+ * accept_count (+= n_steps: every draw moves), evals_total, draws/thin, chain_s1/chain_s2 (+shift) are
+ * honoured; trace: zp receives the accepted line coordinate x1, z_init the exponential e, u the interval
+ * uniform, plus evals, rho, slice_u, slice_n. */
+int klhr_slice_run(const klhr_model_t* model, const klhr_slice_t* slice, const klhr_direction_t* dir, int dtype,
+                   void* theta_dev, int64_t n_chains, int64_t chain_offset, int64_t draw_offset, int32_t n_steps,
+                   uint64_t seed, const klhr_accum_t* accum, const klhr_trace_t* trace, void* stream);
+
+/* One Slice._uni_slice (slice.py:84-146) for every chain with HOST-INJECTED direction and variates:
+ * rho [B][D], e [B] standard exponentials, u0 [B] uniforms behind rng.uniform(0, w), shrink_u [B][cap]
+ * uniforms behind the shrinkage proposals rng.uniform(L, R) (NaN = none left: the chain stays put and
+ * reports slice_n = cap + 1).  theta is advanced in place. */
+int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int dtype, void* theta_dev,
+                      const void* rho_dev, const void* e_dev, const void* u0_dev, const void* shrink_u_dev,
+                      const klhr_trace_t* trace, int64_t n_chains, void* stream);
 
 /* Pooled second-moment accumulation for the adaptation PCA (replaces the per-sample CCIPCA
  * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,

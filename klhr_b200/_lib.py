@@ -16,6 +16,7 @@ LIB_PATH = _HERE / "libklhr_sm100.so"
 KLHR_F64, KLHR_F32 = 0, 1
 FAMILY_GAUSS, FAMILY_SINH = 0, 1
 MAX_NODES = 32
+ABI_VERSION = 2
 
 MODEL_IDS = {"normal": 0, "ill-normal": 1, "funnel": 2, "corr-normal": 3, "ar1": 4, "arK": 5,
              "rosenbrock": 6, "earnings": 7}
@@ -44,7 +45,12 @@ class TraceDesc(C.Structure):
     _fields_ = [("eta", C.c_void_p), ("zp", C.c_void_p), ("r", C.c_void_p), ("accept", C.c_void_p),
                 ("evals", C.c_void_p), ("rho", C.c_void_p), ("z_init", C.c_void_p),
                 ("z_prop", C.c_void_p), ("u", C.c_void_p), ("init4", C.c_void_p), ("or_r", C.c_void_p),
-                ("or_v", C.c_void_p)]
+                ("or_v", C.c_void_p), ("slice_u", C.c_void_p), ("slice_n", C.c_void_p)]
+
+
+class SliceDesc(C.Structure):
+    _fields_ = [("w", C.c_double), ("lower", C.c_double), ("upper", C.c_double), ("tol", C.c_double),
+                ("cap", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AccumDesc(C.Structure):
@@ -67,6 +73,12 @@ EXPORTS = {
                            C.POINTER(AccumDesc), C.POINTER(TraceDesc), C.c_void_p]),
     "klhr_mh_run": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.c_int64,
                               C.c_int32, C.c_uint64, C.POINTER(AccumDesc), C.POINTER(TraceDesc), C.c_void_p]),
+    "klhr_slice_run": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SliceDesc), C.POINTER(DirectionDesc), C.c_int,
+                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_uint64,
+                                 C.POINTER(AccumDesc), C.POINTER(TraceDesc), C.c_void_p]),
+    "klhr_slice_replay": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SliceDesc), C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TraceDesc), C.c_int64,
+                                    C.c_void_p]),
     "klhr_outer_accumulate": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_outer_scratch_doubles": (C.c_int64, [C.c_int64, C.c_int32]),
@@ -96,7 +108,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.klhr_abi_version() != 1:
+    if lib.klhr_abi_version() != ABI_VERSION:
         raise KLHRLibraryError("libklhr_sm100.so ABI version mismatch")
     _lib = lib
     return lib

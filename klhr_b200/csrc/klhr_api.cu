@@ -8,6 +8,7 @@
 
 #include "klhr_chain.cuh"
 #include "klhr_mh.cuh"
+#include "klhr_slice.cuh"
 
 namespace klhr {
 
@@ -350,6 +351,84 @@ int klhr_mh_run(const klhr_model_t* model, int dtype, void* theta_dev, double st
         case KLHR_MODEL_EARNINGS: e = launch_mh_earnings(a, dtype, st); break;
     }
     return cuda_fail(e, "klhr_mh_run");
+}
+
+static int check_slice(const klhr_slice_t* sp) {
+    if (!sp) return fail(-1, "slice must not be NULL");
+    if (!(sp->w > 0) || !std::isfinite(sp->w)) return fail(-15, "slice: w must be positive and finite");
+    if (!(sp->lower <= 0.0) || !(sp->upper >= 0.0)) return fail(-15, "slice: need lower <= 0 <= upper (the current point is line coordinate 0)");
+    if (!(sp->tol >= 0)) return fail(-15, "slice: tol must be non-negative");
+    if (sp->cap < 1) return fail(-15, "slice: cap must be >= 1");
+    return 0;
+}
+
+static int dispatch_slice(const SliceArgs& a, int dtype, bool replay, cudaStream_t st) {
+    switch (a.mp.id) {
+        case KLHR_MODEL_NORMAL: return launch_slice_normal(a, dtype, replay, st);
+        case KLHR_MODEL_ILL_NORMAL: return launch_slice_ill_normal(a, dtype, replay, st);
+        case KLHR_MODEL_FUNNEL: return launch_slice_funnel(a, dtype, replay, st);
+        case KLHR_MODEL_CORR_NORMAL: return launch_slice_corr_normal(a, dtype, replay, st);
+        case KLHR_MODEL_AR1: return launch_slice_ar1(a, dtype, replay, st);
+        case KLHR_MODEL_ARK: return launch_slice_ark(a, dtype, replay, st);
+        case KLHR_MODEL_ROSENBROCK: return launch_slice_rosenbrock(a, dtype, replay, st);
+        case KLHR_MODEL_EARNINGS: return launch_slice_earnings(a, dtype, replay, st);
+    }
+    return -2;
+}
+
+int klhr_slice_run(const klhr_model_t* model, const klhr_slice_t* slice, const klhr_direction_t* dir, int dtype,
+                   void* theta_dev, int64_t n_chains, int64_t chain_offset, int64_t draw_offset, int32_t n_steps,
+                   uint64_t seed, const klhr_accum_t* accum, const klhr_trace_t* trace, void* stream) {
+    SliceArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_slice(slice)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains < 0 || n_steps < 0 || chain_offset < 0 || draw_offset < 0) return fail(-10, "negative count or offset");
+    if (dir) {
+        a.dir = *dir;
+        if (a.dir.mean_cols && a.dir.n_cols < 1) return fail(-11, "direction: n_cols must be >= 1 with mean_cols");
+        if (a.dir.n_zero_cols < 0 || a.dir.n_zero_cols > 1 || (a.dir.mean_cols && a.dir.n_zero_cols >= a.dir.n_cols))
+            return fail(-11, "direction: n_zero_cols must be 0 or 1 and smaller than n_cols");
+        if (a.dir.mean_cols && a.dir.n_cols > 1 && !a.dir.cdf) return fail(-11, "direction: cdf needed when n_cols > 1");
+        if (!a.dir.mean_cols) a.dir.n_cols = 0;
+    }
+    a.acc.thin = 1;
+    if (accum) {
+        a.acc = *accum;
+        if (a.acc.thin < 1) a.acc.thin = 1;
+        if (a.acc.pooled_s1 || a.acc.pooled_s2) return fail(-12, "klhr_slice_run: pooled in-kernel moments are not supported");
+        if (a.acc.chain_s2 && !a.acc.chain_s1) return fail(-12, "chain_s2 needs chain_s1");
+    }
+    if (trace) a.tr = *trace;
+    if (n_chains == 0 || n_steps == 0) return 0;
+    if (!theta_dev) return fail(-1, "theta must not be NULL");
+    a.sp = *slice; a.tol = slice->tol;
+    a.theta = theta_dev; a.B = n_chains;
+    a.chain_offset = chain_offset; a.draw_offset = draw_offset; a.n_steps = n_steps; a.seed = seed;
+    return cuda_fail(dispatch_slice(a, dtype, false, (cudaStream_t)stream), "klhr_slice_run");
+}
+
+int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int dtype, void* theta_dev,
+                      const void* rho_dev, const void* e_dev, const void* u0_dev, const void* shrink_u_dev,
+                      const klhr_trace_t* trace, int64_t n_chains, void* stream) {
+    SliceArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_slice(slice)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    if (n_chains == 0) return 0;
+    if (!theta_dev || !rho_dev || !e_dev || !u0_dev || !shrink_u_dev)
+        return fail(-1, "theta, rho, e, u0, shrink_u must not be NULL");
+    a.sp = *slice; a.tol = slice->tol;
+    a.theta = theta_dev; a.B = n_chains;
+    a.rho = rho_dev; a.e = e_dev; a.u0 = u0_dev; a.shrink_u = shrink_u_dev;
+    a.n_steps = 1;
+    a.acc.thin = 1;
+    if (trace) a.tr = *trace;
+    a.tr.slice_u = nullptr;                                       // input in this mode
+    return cuda_fail(dispatch_slice(a, dtype, true, (cudaStream_t)stream), "klhr_slice_replay");
 }
 
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running, int accumulate,

@@ -39,10 +39,12 @@ template <typename R> struct Num;
 template <> struct Num<double> {
     static constexpr double eps = 2.220446049250313e-16;
     __device__ static __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    __device__ static __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 };
 template <> struct Num<float> {
     static constexpr float eps = 1.1920929e-07f;
     __device__ static __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    __device__ static __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
 };
 
 __device__ __forceinline__ double r_exp(double x) { return exp(x); }

@@ -61,6 +61,48 @@ __host__ __device__ inline int pad_dim(int D, int real_bytes) {
     return p;
 }
 
+// Direction of one chain, by its octet (reference _random_direction, klhr.py:143-153): mean column
+// j = searchsorted(cdf, u_col, 'right'), x = mean_j + sd z with z from the chain's Philox stream,
+// rho = x / ||x + tol|| left in rh[0..D).  Element i = g0 + lane + 32 t + 8 r  <->  Philox slot
+// kSlotDir + lane + 8 t + g0 / 4, word r; x is formed in fp32 (same stream and rounding as the tile kernel).
+template <typename R>
+__device__ __forceinline__ void octet_direction(const klhr_direction_t& dir, const R* s_sd, const R* s_mean, R* rh,
+                                                int D, R tol, R u_col, uint32_t c0, uint32_t c1, uint32_t d0,
+                                                uint32_t k0, uint32_t k1d, int lane, unsigned om) {
+    const R* mcol = nullptr;
+    if (dir.mean_cols) {
+        int j = 0;
+        if (dir.n_cols > 1) {
+            const R* cdf = reinterpret_cast<const R*>(dir.cdf);
+            while (j < dir.n_cols - 1 && u_col >= cdf[j]) ++j;
+        }
+        mcol = j < dir.n_cols - dir.n_zero_cols ? s_mean + (size_t)j * D : nullptr;   // zero column
+    }
+    R ss = 0;
+    for (int g0 = 0; g0 < D; g0 += 128) {
+        for (int t = 0; t < 4 && g0 + 32 * t < D; ++t) {
+            uint32_t w[4];
+            Philox::block(c0, c1, d0, kSlotDir + (uint32_t)(lane + 8 * t) + (uint32_t)(g0 / 4), k0, k1d, w);
+            float z[4];
+            box_muller_f32(w[0], w[1], z[0], z[1]);
+            box_muller_f32(w[2], w[3], z[2], z[3]);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = g0 + lane + 32 * t + 8 * rr;
+                if (i < D) {
+                    const R x = (R)fmaf((float)s_sd[i], z[rr], mcol ? (float)mcol[i] : 0.0f);
+                    rh[i] = x;
+                    const R xt = x + tol;
+                    ss += xt * xt;
+                }
+            }
+        }
+    }
+    ss = oct_sum(ss, om);
+    const R inv = R(1) / r_sqrt(ss);
+    for (int i = lane; i < D; i += kOct) rh[i] *= inv;
+}
+
 template <typename R, typename Model, int NE, bool kReplay, bool kAccum>
 __global__ void __launch_bounds__(kThreadsMax, step_min_ctas<R, Model>()) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,41 +215,7 @@ __global__ void __launch_bounds__(kThreadsMax, step_min_ctas<R, Model>()) step_k
                 u = oct_bcast(sv0, 2, om);
                 init2 = oct_bcast(sv0, 3, om);
                 init3 = oct_bcast(sv1, 3, om);
-                // mean column (klhr.py:146-148): searchsorted(cdf, u, 'right')
-                const R* mcol = nullptr;
-                if (a.dir.mean_cols) {
-                    int j = 0;
-                    if (a.dir.n_cols > 1) {
-                        const R* cdf = reinterpret_cast<const R*>(a.dir.cdf);
-                        while (j < a.dir.n_cols - 1 && u_col >= cdf[j]) ++j;
-                    }
-                    mcol = j < a.dir.n_cols - a.dir.n_zero_cols ? s_mean + (size_t)j * D : nullptr;   // zero column
-                }
-                R ss = 0;
-                // element i = g0 + lane + 32 t + 8 r  <->  Philox slot kSlotDir + lane + 8 t + g0 / 4,
-                // word r; x is formed in fp32 (same stream and rounding as the tile kernel)
-                for (int g0 = 0; g0 < D; g0 += 128) {
-                    for (int t = 0; t < 4 && g0 + 32 * t < D; ++t) {
-                        uint32_t w[4];
-                        Philox::block(c0, c1, d0, kSlotDir + (uint32_t)(lane + 8 * t) + (uint32_t)(g0 / 4), k0, k1d, w);
-                        float z[4];
-                        box_muller_f32(w[0], w[1], z[0], z[1]);
-                        box_muller_f32(w[2], w[3], z[2], z[3]);
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) {
-                            const int i = g0 + lane + 32 * t + 8 * rr;
-                            if (i < D) {
-                                const R x = (R)fmaf((float)s_sd[i], z[rr], mcol ? (float)mcol[i] : 0.0f);
-                                rh[i] = x;
-                                const R xt = x + tol;
-                                ss += xt * xt;
-                            }
-                        }
-                    }
-                }
-                ss = oct_sum(ss, om);
-                const R inv = R(1) / r_sqrt(ss);
-                for (int i = lane; i < D; i += kOct) rh[i] *= inv;
+                octet_direction<R>(a.dir, s_sd, s_mean, rh, D, tol, u_col, c0, c1, d0, k0, k1d, lane, om);
                 if (a.tr.z_init) {
                     if (lane == 0) {
                         reinterpret_cast<R*>(a.tr.z_init)[row] = z_init;

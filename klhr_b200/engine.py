@@ -95,7 +95,7 @@ def _require_cuda(t, name):
 class Trace:
     """Per-draw trace buffers [S, B, ...] allocated on the device."""
 
-    def __init__(self, S, B, D, n_eta, dtype, device, variates=False, rho=True):
+    def __init__(self, S, B, D, n_eta, dtype, device, variates=False, rho=True, slice_cap=0):
         z = lambda *shape, dt=dtype: torch.zeros(*shape, dtype=dt, device=device)
         self.eta = z(S, B, n_eta)
         self.zp = z(S, B)
@@ -109,12 +109,15 @@ class Trace:
         self.init4 = z(S, B, 4) if variates and n_eta == 4 else None
         self.or_r = z(S, B, dt=torch.int32) if variates else None
         self.or_v = z(S, B) if variates else None
+        self.slice_u = z(S, B, slice_cap) if slice_cap > 0 and variates else None
+        self.slice_n = z(S, B, dt=torch.int32) if slice_cap > 0 else None
 
     def descriptor(self):
         return _lib.TraceDesc(eta=_ptr(self.eta), zp=_ptr(self.zp), r=_ptr(self.r), accept=_ptr(self.accept),
                               evals=_ptr(self.evals), rho=_ptr(self.rho), z_init=_ptr(self.z_init),
                               z_prop=_ptr(self.z_prop), u=_ptr(self.u), init4=_ptr(self.init4),
-                              or_r=_ptr(self.or_r), or_v=_ptr(self.or_v))
+                              or_r=_ptr(self.or_r), or_v=_ptr(self.or_v), slice_u=_ptr(self.slice_u),
+                              slice_n=_ptr(self.slice_n))
 
 
 def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, init4=None, trace=True,
@@ -195,6 +198,75 @@ def run(model: BSModel, fit: FitConfig, theta, n_steps, seed, direction: Directi
                                 C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ad),
                                 C.byref(trd) if trd else None, st),
                    "klhr_run")
+
+
+@dataclass
+class SliceConfig:
+    """Reference ``Slice`` constructor arguments that reach ``_uni_slice`` (slice.py:14-39); ``m = inf`` only
+    (the configuration the reference itself can run).  ``cap``: columns of the shrinkage-uniform trace."""
+    w: float = 1.0
+    lower: float = -np.inf
+    upper: float = np.inf
+    tol: float = 1e-12
+    cap: int = 24
+
+    def __post_init__(self):
+        if not (self.w > 0 and np.isfinite(self.w)):
+            raise ValueError("w must be positive and finite")
+        if not (self.lower <= 0.0 <= self.upper):
+            raise ValueError("need lower <= 0 <= upper: the current point is line coordinate 0")
+
+    def descriptor(self):
+        return _lib.SliceDesc(w=float(self.w), lower=float(self.lower), upper=float(self.upper),
+                              tol=float(self.tol), cap=int(self.cap), reserved=0)
+
+
+def slice_replay(model: BSModel, cfg: SliceConfig, theta, rho, e, u0, shrink_u):
+    """One ``Slice._uni_slice`` (slice.py:84-146) for every chain with host-injected direction and variates;
+    ``theta`` (B, D) is advanced IN PLACE.  ``shrink_u`` (B, cap) holds the uniforms behind the shrinkage
+    proposals, NaN-padded.  Returns a ``Trace`` (zp = accepted line coordinate, evals, slice_n)."""
+    lib = _lib.load()
+    for t, n in ((theta, "theta"), (rho, "rho"), (e, "e"), (u0, "u0"), (shrink_u, "shrink_u")):
+        _require_cuda(t, n)
+    B, D = theta.shape
+    if D != model.dim():
+        raise ValueError("theta does not match model.dim()")
+    if tuple(shrink_u.shape) != (B, cfg.cap):
+        raise ValueError("shrink_u must have shape (B, cfg.cap)")
+    dtype, dev = theta.dtype, theta.device
+    tr = Trace(1, B, D, 0, dtype, dev, rho=False, slice_cap=cfg.cap)
+    trd = tr.descriptor()
+    md, sd = model.descriptor(dtype, dev), cfg.descriptor()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.klhr_slice_replay(C.byref(md), C.byref(sd), _dtype_code(dtype), theta.data_ptr(),
+                                         rho.data_ptr(), e.data_ptr(), u0.data_ptr(), shrink_u.data_ptr(),
+                                         C.byref(trd), B, st), "klhr_slice_replay")
+    return tr
+
+
+def slice_run(model: BSModel, cfg: SliceConfig, theta, n_steps, seed, direction: Direction = None,
+              chain_offset=0, draw_offset=0, *, shift=None, chain_s1=None, chain_s2=None, accept_count=None,
+              evals_total=None, draws=None, thin=1, thin_offset=0, trace: Trace = None):
+    """``n_steps`` slice-sampling draws along random directions for every chain, in place on ``theta``."""
+    lib = _lib.load()
+    _require_cuda(theta, "theta")
+    B, D = theta.shape
+    if D != model.dim():
+        raise ValueError("theta does not match model.dim()")
+    dtype, dev = theta.dtype, theta.device
+    md, sd = model.descriptor(dtype, dev), cfg.descriptor()
+    dd = (direction or Direction()).descriptor()
+    ad = _lib.AccumDesc(shift=_ptr(shift), chain_s1=_ptr(chain_s1), chain_s2=_ptr(chain_s2),
+                        accept_count=_ptr(accept_count), evals_total=_ptr(evals_total), draws=_ptr(draws),
+                        thin=int(thin), skip_accum_last=0, thin_offset=int(thin_offset))
+    trd = trace.descriptor() if trace is not None else None
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.klhr_slice_run(C.byref(md), C.byref(sd), C.byref(dd), _dtype_code(dtype), theta.data_ptr(),
+                                      B, int(chain_offset), int(draw_offset), int(n_steps),
+                                      C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ad),
+                                      C.byref(trd) if trd else None, st), "klhr_slice_run")
 
 
 def outer_scratch(theta):

@@ -8,7 +8,7 @@ scripts, without the plots (matplotlib is not a dependency here).
 
 Flags and defaults are those of reference ``experiment_accuracy.py:14-25``, ``experiment_ar1.py:16-28``,
 ``experiment_funnel.py:15-26`` and ``experiment_relaxationtime.py:14-26``; ``ALGO`` is ``klhr``, ``klhr_sinh``,
-``sub_klhr_sinh`` or (accuracy only, as the comparison arm) ``mh``.  Added: ``--chains`` (every metric is
+``sub_klhr_sinh``, ``slice`` or (accuracy only, as the comparison arm) ``mh``.  Added: ``--chains`` (every metric is
 averaged over that many independent chains), ``--data`` (Stan JSON file), ``--seed``, ``--out`` (JSON file).
 Each command prints one JSON object with the quantities the reference plots or prints under ``-v``
 (acceptance rate, MSJD, RMSE of running means / variances, posterior summaries, gradient evaluations).
@@ -23,9 +23,9 @@ import click
 import numpy as np
 import torch
 
-from . import BSModel, KLHR, KLHRSINH, MH, SUBKLHRSINH
+from . import BSModel, KLHR, KLHRSINH, MH, SUBKLHRSINH, Slice
 
-ALGOS = {"klhr": KLHR, "klhr_sinh": KLHRSINH, "sub_klhr_sinh": SUBKLHRSINH}
+ALGOS = {"klhr": KLHR, "klhr_sinh": KLHRSINH, "sub_klhr_sinh": SUBKLHRSINH, "slice": Slice}
 
 
 def common(fn):

@@ -154,10 +154,7 @@ class KLHR(MCMCBase):
                 kw.update(shift=self._shift_dev, pooled_s1=mom.s1, pooled_s2=mom.s2, skip_accum_last=closes)
             elif chain_s1 is not None:
                 kw.update(shift=stat_shift, chain_s1=chain_s1, chain_s2=chain_s2)
-            engine.run(self.model, self._fit, self._theta, steps, self.seed, self._direction,
-                       chain_offset=self._chain_offset, draw_offset=self._draw,
-                       accept_count=self._accept_count, evals_total=self._evals_total,
-                       draws=draws, thin=thin, thin_offset=done, **kw)
+            self._launch(steps, draws=draws, thin=thin, thin_offset=done, **kw)
             if adapting and self._overrelaxed and self._adapt_K:
                 # pooled Smoother signal (klhr.py:219-221): +1 for a chain that moved, -1 otherwise
                 acc_now = float(self._accept_count.double().mean())
@@ -174,6 +171,12 @@ class KLHR(MCMCBase):
                     self._close_window()
                 else:
                     self._snapshot_update()
+
+    def _launch(self, steps, **kw):
+        """``steps`` draws for every chain in one launch (subclasses swap the transition kernel)."""
+        engine.run(self.model, self._fit, self._theta, steps, self.seed, self._direction,
+                   chain_offset=self._chain_offset, draw_offset=self._draw,
+                   accept_count=self._accept_count, evals_total=self._evals_total, **kw)
 
     def _snapshot_update(self):
         """Pooled analogue of klhr.py:216-219 on the current ensemble: PCA second moments of

@@ -468,3 +468,59 @@ def step(model, theta, rho, z_init, z_prop, u, cfg: FitConfig, init4=None, xw=No
         accept = np.log(u) < np.minimum(0.0, r)              # NaN compares False -> reject
     theta1 = np.where(accept[:, None], theta + zp[:, None] * rho, theta)
     return dict(eta=eta, zp=zp, r=r, accept=accept, theta=theta1, evals=evals + 2, converged=conv)
+
+
+# ------------------------------------------------------------------ slice sampling along a line (N3)
+def slice_step(model, theta, rho, e, u0, shrink_u, w=1.0, lower=-np.inf, upper=np.inf, max_out=1 << 20):
+    """One draw of the reference's ``Slice._uni_slice`` (slice.py:84-146, ``m = inf``) for every chain, with
+    injected variates: ``e`` (B,) standard exponentials, ``u0`` (B,) the uniform behind
+    ``rng.uniform(0, w)``, ``shrink_u`` (B, S) the uniforms behind the shrinkage proposals
+    ``rng.uniform(L, R) = L + (R - L) u`` (NaN = not available).  Returns x1 (accepted line coordinate),
+    theta after the move, n_shrink (proposals consumed), evals (value calls: 1 + stepping-out tests +
+    proposals), L, R (the interval the accepted proposal was drawn from).  A chain that exhausts its
+    ``shrink_u`` keeps x1 = 0 and reports n_shrink = S + 1."""
+    theta = np.asarray(theta, dtype=np.float64)
+    rho = np.asarray(rho, dtype=np.float64)
+    B = theta.shape[0]
+    e, u0 = np.asarray(e, dtype=np.float64), np.asarray(u0, dtype=np.float64)
+    g = lambda y: line_eval(model, theta, rho, y)[0]          # l(y) - l(0); -inf on failure
+    logy = -e                                                  # gx0 - e with gx0 = l(0) - l(0) = 0
+    off = w * u0
+    L = 0.0 - off
+    R = 0.0 + (w - off)
+    evals = np.ones(B, dtype=np.int64)
+    for side in (0, 1):                                        # stepping out (slice.py:95-107)
+        act = np.ones(B, dtype=bool)
+        for _ in range(max_out):
+            act &= (L > lower) if side == 0 else (R < upper)
+            if not act.any():
+                break
+            val = g(L if side == 0 else R)
+            evals += act
+            act &= ~(val <= logy)
+            if side == 0:
+                L = np.where(act, L - w, L)
+            else:
+                R = np.where(act, R + w, R)
+    L = np.maximum(L, lower)                                   # slice.py:127-128
+    R = np.minimum(R, upper)
+    x1 = np.zeros(B)
+    done = np.zeros(B, dtype=bool)
+    n_shrink = np.zeros(B, dtype=np.int64)
+    for k in range(shrink_u.shape[1]):                         # shrinkage (slice.py:131-139)
+        uk = shrink_u[:, k]
+        act = ~done & ~np.isnan(uk)
+        if not act.any():
+            break
+        cand = L + (R - L) * np.where(act, uk, 0.0)
+        val = g(cand)
+        evals += act
+        n_shrink += act
+        ok = act & (val >= logy)
+        x1 = np.where(ok, cand, x1)
+        done |= ok
+        rej = act & ~ok
+        R = np.where(rej & (cand > 0.0), cand, R)
+        L = np.where(rej & ~(cand > 0.0), cand, L)
+    n_shrink = np.where(done, n_shrink, shrink_u.shape[1] + 1)
+    return dict(x1=x1, theta=theta + x1[:, None] * rho, n_shrink=n_shrink, evals=evals, L=L, R=R, done=done)

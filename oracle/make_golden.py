@@ -50,7 +50,14 @@ class TapeRNG:
     def uniform(self, low=0.0, high=1.0, size=None):
         u = self._g.random(size)
         self.log.append(("uniform", np.array(u, dtype=np.float64, copy=True)))
-        return low + (high - low) * u
+        self.last_uniform_value = low + (high - low) * u
+        return self.last_uniform_value
+
+    # reference call site: slice.py:90
+    def exponential(self):
+        e = self._g.standard_exponential()
+        self.log.append(("exponential", np.array(e, dtype=np.float64)))
+        return e
 
     # reference call site: klhr.py:147 ; searchsorted(cumsum(p), u, 'right') is what NumPy does
     def choice(self, a, p=None):
@@ -154,6 +161,71 @@ def _tape_run(algo, M, family):
     return out
 
 
+SLICE_MAX_SHRINK = 24
+
+
+def _tape_slice(algo, M):
+    """Tape of the reference ``Slice`` (slice.py): per draw theta0, rho, the exponential e, the interval
+    uniform u0, the shrinkage uniforms (padded with NaN), the accepted line coordinate x1 and the number
+    of model value calls; adaptation state after every closure."""
+    rec = {k: [] for k in ("theta0", "rho", "e", "u0", "shrink_u", "n_shrink", "x1", "evals", "ujdir")}
+    closures = {"draw": [], "mean": [], "cov": [], "eigvecs": [], "eigvals": []}
+    cur = {}
+    orig = algo._uni_slice
+
+    def uni(rho):
+        n0 = len(algo.rng.log)
+        c0 = algo.model.n_value_calls
+        theta0 = np.array(algo.theta, copy=True)
+        out = orig(rho)
+        used = algo.rng.log[n0:]
+        assert used[0][0] == "exponential" and all(k == "uniform" for k, _ in used[1:])
+        su = np.full(SLICE_MAX_SHRINK, np.nan)
+        sh = [float(v) for _, v in used[2:]]
+        assert len(sh) <= SLICE_MAX_SHRINK
+        su[:len(sh)] = sh
+        cur.update(theta0=theta0, rho=np.array(rho, copy=True), e=float(used[0][1]), u0=float(used[1][1]),
+                   shrink_u=su, n_shrink=len(sh), x1=float(algo.rng.last_uniform_value),
+                   evals=algo.model.n_value_calls - c0)
+        return out
+
+    algo._uni_slice = uni
+    for m in range(M):
+        n0 = len(algo.rng.log)
+        wa = algo._windowedadaptation
+        will_close = (wa._warmup >= wa._windowsize and wa._num_windows > 0
+                      and (algo._draw + 1) == wa._closures[wa._idx])
+        algo.draw()
+        first = algo.rng.log[n0]
+        rec["ujdir"].append(float(first[1][0]) if first[0] == "choice" else -1.0)
+        for k in rec:
+            if k != "ujdir":
+                rec[k].append(cur[k])
+        if will_close:
+            closures["draw"].append(algo._draw)
+            closures["mean"].append(np.array(algo._mean, copy=True))
+            closures["cov"].append(np.array(algo._cov, copy=True))
+            closures["eigvecs"].append(np.array(algo._eigvecs, copy=True))
+            closures["eigvals"].append(np.array(algo._eigvals, copy=True))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["theta_last"] = np.array(algo.theta, copy=True)
+    for k, v in closures.items():
+        out["closure_" + k] = np.array(v)
+    out["acceptance_probability"] = np.array(float(algo.acceptance_probability))
+    return out
+
+
+# reference slice.py (N3): name, stan stem, data, draws, ctor kwargs
+SLICE_CASES = [
+    ("slice_normal_d2", "normal", {"D": 2}, 2_000, dict(seed=121)),
+    ("slice_funnel_d2", "funnel", {"D": 1}, 2_000, dict(seed=122)),
+    ("slice_funnel_d11", "funnel", {"D": 10}, 1_000, dict(seed=123, warmup=400)),
+    ("slice_illnormal_d100", "ill-normal", {"D": 100}, 300, dict(seed=124, warmup=200)),
+    ("slice_rosenbrock_d4_w3", "rosenbrock", {"D": 2}, 1_000, dict(seed=125, w=3.0)),
+    ("slice_ark_t200_method2", "arK", "arK.json", 500, dict(seed=126, eigen_method_one=False, warmup=200)),
+    ("stats_slice_funnel_d2_noadapt", "funnel", {"D": 1}, 30_000, dict(seed=127, warmup=0)),
+]
+
 CASES = [
     # name, stan stem, data, family, draws, ctor kwargs, tighten-gtol
     ("normal_d2_klhr", "normal", {"D": 2}, "gauss", 10_000, dict(seed=20261018), None),
@@ -203,6 +275,9 @@ FREERUNS = [
     # random-walk Metropolis (reference mh.py), stepsize of experiment_accuracy.py:69
     ("freerun_normal_d2_mh", "normal", {"D": 2}, "mh", 3000, dict(seed=7, stepsize=0.09)),
     ("freerun_funnel_d2_mh", "funnel", {"D": 1}, "mh", 3000, dict(seed=8, stepsize=0.9)),
+    # slice sampling along adapted directions (reference slice.py)
+    ("freerun_funnel_d2_slice_adapt", "funnel", {"D": 1}, "slice", 400, dict(seed=9, warmup=200)),
+    ("freerun_illnormal_d20_slice_adapt", "ill-normal", {"D": 20}, "slice", 250, dict(seed=10, warmup=200)),
 ]
 
 
@@ -234,6 +309,9 @@ def main():
         if family == "mh":
             import mh as ref_mh
             algo = ref_mh.MH(model, kw["stepsize"], seed=kw["seed"])
+        elif family == "slice":
+            import slice as ref_slice
+            algo = ref_slice.Slice(model, **kw)
         else:
             cls = ref_klhr.KLHR if family == "gauss" else ref_sinh.KLHRSINH
             (ref_klhr if family == "gauss" else ref_sinh).minimize = scipy.optimize.minimize
@@ -247,6 +325,31 @@ def main():
                             grad_evals=np.array(int(getattr(algo, "grad_evals", 0))), meta_json=np.array(json.dumps(meta)),
                             data_json=np.array(json.dumps(data)))
         print(f"{name:36s} draws={M:6d} acc={float(np.ravel(algo.acceptance_probability)[0]):.3f}")
+
+    for name, stem, data, M, kw in SLICE_CASES:
+        if args.only and args.only not in name:
+            continue
+        import slice as ref_slice
+        if isinstance(data, str):
+            data = json.loads((ref / "stan" / data).read_text())
+        model = shim.BSModel(stan_file=f"stan/{stem}.stan", data=data)
+        kw = dict(kw)
+        seed = kw.pop("seed")
+        algo = ref_slice.Slice(model, seed=seed, **kw)
+        algo.rng = TapeRNG(seed + 1000)
+        tape = _tape_slice(algo, M)
+        if name.startswith("stats_"):
+            tape = {"theta_thin10": tape["theta0"][::10], "theta_last": tape["theta_last"],
+                    "evals_mean": np.array(tape["evals"].mean()), "n_shrink_mean": np.array(tape["n_shrink"].mean()),
+                    "acceptance_probability": tape["acceptance_probability"]}
+        meta = dict(case=name, model=stem, family="slice", draws=M, ctor=dict(kw, seed=seed), numpy=np.__version__,
+                    w=float(algo.w), tol=float(algo._tol), initscale=float(algo._initscale), J=int(algo.J),
+                    eigen_method_one=bool(algo._eigen_method_one),
+                    closures=list(algo._windowedadaptation._closures))
+        tape["meta_json"] = np.array(json.dumps(meta))
+        tape["data_json"] = np.array(json.dumps(data))
+        np.savez_compressed(out_dir / f"{name}.npz", **tape)
+        print(f"{name:32s} draws={M:6d} evals/draw={float(np.mean(tape.get('evals', tape.get('evals_mean')))):.2f}")
 
     for name, stem, data, family, M, kw, gtol in CASES:
         if args.only and args.only not in name:

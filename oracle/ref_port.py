@@ -249,6 +249,8 @@ class ChainSampler:
     (``klhr.py:212-214``) is not ported: K stays at its constructor value.
     """
 
+    clip_J = True
+
     def __init__(self, model, family="gauss", theta=None, seed=None, rng=None, N=8, K=10, J=2,
                  l=4, initscale=0.1, warmup=1_000, windowsize=50, windowscale=2, tol=None,
                  grad_clip=1e15, scale_clip=None, scale_dir_cov=False, overrelaxed=False,
@@ -264,7 +266,7 @@ class ChainSampler:
         self.rng = rng if rng is not None else np.random.default_rng(seed)
         self.family_name = family
         self.N = N
-        self.J = (J if J < self.D else self.D - 1) if gauss else J     # klhr.py:39 vs klhr_sinh.py:37
+        self.J = (J if J < self.D else self.D - 1) if (gauss and self.clip_J) else J   # klhr.py:39 vs klhr_sinh.py:37, slice.py:41
         self.tol, self.initscale = tol, initscale
         self.x, self.w = gauss_hermite_probabilists(N)
         self.line = {"gauss": GaussLine, "sinh": SinhLine, "subsinh": SubSinhLine}[family](
@@ -375,13 +377,17 @@ class ChainSampler:
                          accept=bool(np.ravel(a)[0]))
         return self.theta
 
+    def transition(self, rho):
+        eta = self.fit(rho)
+        theta = self.metropolis(eta, rho)
+        self.last.update(rho=rho, eta=eta)
+        return theta
+
     # ------------------------------------------------------------------------ draw (H9)
     def draw(self):
         self.n_draw += 1
         rho = self.random_direction()
-        eta = self.fit(rho)
-        theta = self.metropolis(eta, rho)
-        self.last.update(rho=rho, eta=eta)
+        theta = self.transition(rho)
         if self.schedule.window_closed(self.n_draw):
             self.dir_mean = self.mom_theta.mean()
             self.dir_cov = self.mom_theta.var()
@@ -405,6 +411,58 @@ class ChainSampler:
         for m in range(1, M):
             out[m] = self.draw()
         return out
+
+
+class SliceChain(ChainSampler):
+    """Univariate slice sampling (stepping out + shrinkage, Neal 2003) along KLHR's adapted random
+    directions: port of reference ``slice.py:12-167`` for its working configuration ``m = inf``
+    (the finite-``m`` branch of the reference raises NameError, slice.py:108,124).  Direction law and
+    windowed adaptation are the KLHR ones (slice.py:148-176 == klhr.py:143-153,196-223) except that J
+    is not clipped to D - 1 (slice.py:41).  Generator call order per draw: [choice], multivariate_normal,
+    exponential, uniform(0, w), then one uniform(L, R) per shrinkage proposal."""
+    clip_J = False
+
+    def __init__(self, model, w=1, lower=-np.inf, upper=np.inf, tol=1e-12, **kw):
+        super().__init__(model, family="gauss", tol=tol, **kw)
+        self.w, self.lower, self.upper = w, lower, upper
+        self.last = {}
+
+    def transition(self, rho):                                           # _uni_slice, slice.py:84-146
+        g = lambda x: self.model.log_density(rho * x + self.theta)
+        n0 = getattr(self.model, "n_value_calls", 0)
+        logy = g(0.0) - self.rng.exponential()
+        u = self.rng.uniform(low=0, high=self.w)
+        L = 0.0 - u
+        R = 0.0 + (self.w - u)
+        while True:                                                      # stepping out, m = inf (:95-107)
+            if L <= self.lower:
+                break
+            if g(L) <= logy:
+                break
+            L -= self.w
+        while True:
+            if R >= self.upper:
+                break
+            if g(R) <= logy:
+                break
+            R += self.w
+        L = max(L, self.lower)                                           # :127-128
+        R = min(R, self.upper)
+        n_shrink = 0
+        while True:                                                      # shrinkage (:131-139)
+            x1 = self.rng.uniform(low=L, high=R)
+            n_shrink += 1
+            if g(x1) >= logy:
+                break
+            if x1 > 0.0:
+                R = x1
+            else:
+                L = x1
+        self.theta = rho * x1 + self.theta
+        self.acceptance_probability += (1 - self.acceptance_probability) / self.n_draw
+        self.last = dict(rho=rho, x1=x1, L=L, R=R, n_shrink=n_shrink,
+                         evals=getattr(self.model, "n_value_calls", 0) - n0)
+        return self.theta
 
 
 class MHChain:
@@ -485,6 +543,48 @@ def replay_port(tape, model, family, n=None, **kw):
         out["zp"].append(s.last["zp"])
         out["r"].append(s.last["r"])
         out["accept"].append(s.last["accept"])
+        out["theta"].append(np.array(th))
+    out = {k: np.array(v) for k, v in out.items()}
+    out["sampler"] = s
+    return out
+
+
+class SliceReplayRNG:
+    """Plays a slice tape (tests/golden/slice_*.npz) back through the Generator calls ``SliceChain`` makes."""
+
+    def __init__(self, tape):
+        self.t, self.i, self.k = tape, 0, 0
+
+    def choice(self, n, p=None):
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        return int(np.searchsorted(cdf, float(self.t["ujdir"][self.i]), side="right"))
+
+    def exponential(self):
+        return float(self.t["e"][self.i])
+
+    def uniform(self, low=0.0, high=1.0):
+        if self.k == 0:
+            u = float(self.t["u0"][self.i])
+        else:
+            u = float(self.t["shrink_u"][self.i][self.k - 1])
+        self.k += 1
+        return low + (high - low) * u
+
+
+def replay_slice_port(tape, model, n=None, **kw):
+    """Re-run ``SliceChain`` over a slice tape with injected rho / variates."""
+    M = len(tape["e"]) if n is None else n
+    rng = SliceReplayRNG(tape)
+    s = SliceChain(model, theta=tape["theta0"][0], rng=rng, **kw)
+    s.random_direction = lambda: tape["rho"][rng.i]
+    out = dict(x1=[], n_shrink=[], evals=[], theta=[])
+    for i in range(M):
+        rng.i, rng.k = i, 0
+        th = s.draw()
+        out["x1"].append(s.last["x1"])
+        out["n_shrink"].append(s.last["n_shrink"])
+        out["evals"].append(s.last["evals"])
         out["theta"].append(np.array(th))
     out = {k: np.array(v) for k, v in out.items()}
     out["sampler"] = s

@@ -31,6 +31,8 @@ def test_ar1_and_funnel_experiments():
     assert abs(f["x_sd"] - 3.0) < 0.35 and abs(f["x_mean"]) < 0.3 and f["ks_distance_to_N(0,3)"] < 0.06
     s = _run(["funnel", "-M", "600", "-w", "300", "--chains", "256", "--seed", "4", "-o", "sub_klhr_sinh"])
     assert 0.8 < s["acceptance"] <= 1.0
+    sl = _run(["funnel", "-M", "1500", "-w", "500", "--chains", "1024", "--seed", "5", "-e1", "slice"])
+    assert sl["acceptance"] == 1.0 and abs(sl["x_sd"] - 3.0) < 0.35 and sl["ks_distance_to_N(0,3)"] < 0.06
 
 
 def test_relaxation_experiment_on_synthetic_earnings(tmp_path):

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.klhr_abi_version() == 1
+    assert lib.klhr_abi_version() == _lib.ABI_VERSION == 2
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.klhr_model_eval(None, 0, None, None, None, 0, None) < 0
     assert "model is NULL" in _lib.last_error()
@@ -34,15 +34,16 @@ def test_struct_layouts_match_header():
     """ctypes mirrors must have the C sizes (checked by compiling a probe with gcc)."""
     import ctypes as C
     from klhr_b200 import _lib
-    src = '#include <stdio.h>\n#include "klhr_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "klhr_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(klhr_model_t),sizeof(klhr_fit_t),sizeof(klhr_direction_t),sizeof(klhr_trace_t),' \
-          'sizeof(klhr_accum_t));return 0;}'
+          'sizeof(klhr_accum_t),sizeof(klhr_slice_t));return 0;}'
     exe = ROOT / "build" / "abi_probe"
     exe.parent.mkdir(exist_ok=True)
     (exe.parent / "abi_probe.c").write_text(src)
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(exe.parent / "abi_probe.c"), "-o", str(exe)], check=True)
     sizes = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
-    mine = [C.sizeof(t) for t in (_lib.ModelDesc, _lib.FitDesc, _lib.DirectionDesc, _lib.TraceDesc, _lib.AccumDesc)]
+    mine = [C.sizeof(t) for t in (_lib.ModelDesc, _lib.FitDesc, _lib.DirectionDesc, _lib.TraceDesc, _lib.AccumDesc,
+                                     _lib.SliceDesc)]
     assert sizes == mine
 
 

@@ -97,3 +97,39 @@ def test_kl_gradient_and_hessian_against_finite_differences():
             if j == 1:
                 gfd[:, 0] -= g[:, 0]
             assert np.allclose(H[:, :, j], gfd, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["slice_normal_d2", "slice_funnel_d2", "slice_funnel_d11", "slice_illnormal_d100",
+                                  "slice_rosenbrock_d4_w3", "slice_ark_t200_method2"])
+def test_batched_slice_step_matches_reference_tape(tapes, name):
+    """``batched.slice_step`` (the kernel's specification) against the tape of the unmodified reference Slice:
+    the same arithmetic in the same order, so agreement is exact."""
+    t, meta, data = tapes(name)
+    model = stan_models.make_model(meta["model"], data)
+    out = batched.slice_step(model, t["theta0"], t["rho"], t["e"], t["u0"], t["shrink_u"], w=meta["w"])
+    th1 = np.vstack([t["theta0"][1:], t["theta_last"][None]])
+    assert out["done"].all()
+    assert np.array_equal(out["x1"], t["x1"])
+    assert np.array_equal(out["n_shrink"], t["n_shrink"])
+    assert np.array_equal(out["evals"], t["evals"])
+    assert np.array_equal(out["theta"], th1)
+
+
+def test_batched_slice_step_bounds_and_exhausted_tape():
+    model = stan_models.make_model("normal", {"D": 3})
+    rng = np.random.default_rng(5)
+    B = 64
+    theta = rng.normal(size=(B, 3))
+    rho = rng.normal(size=(B, 3))
+    rho /= np.linalg.norm(rho, axis=1, keepdims=True)
+    e, u0 = rng.exponential(size=B), rng.random(B)
+    su = rng.random((B, 40))
+    out = batched.slice_step(model, theta, rho, e, u0, su, w=0.5, lower=-0.25, upper=0.75)
+    assert out["done"].all() and (out["x1"] >= -0.25).all() and (out["x1"] <= 0.75).all()
+    assert (out["L"] >= -0.25).all() and (out["R"] <= 0.75).all()
+    # the accepted point is inside the slice
+    l1, _, _ = batched.line_eval(model, theta, rho, out["x1"])
+    assert (l1 >= -e).all()
+    # a tape without shrinkage uniforms: the chain stays put and reports cap + 1
+    none = batched.slice_step(model, theta, rho, e, u0, np.full((B, 2), np.nan))
+    assert not none["done"].any() and (none["n_shrink"] == 3).all() and np.array_equal(none["theta"], theta)

@@ -66,6 +66,46 @@ def test_mh_port_reproduces_reference(name):
     assert float(np.ravel(s.acceptance_probability)[0]) == float(t["acceptance_probability"])
 
 
+SLICE_TAPES = ["slice_normal_d2", "slice_funnel_d2", "slice_funnel_d11", "slice_illnormal_d100",
+               "slice_rosenbrock_d4_w3", "slice_ark_t200_method2"]
+
+
+@pytest.mark.parametrize("name", SLICE_TAPES)
+def test_slice_port_is_bit_exact_on_reference_tape(tapes, name):
+    """Tape of the unmodified reference ``Slice`` (slice.py) replayed through ``SliceChain``: accepted line
+    coordinates, trajectory, value-call counts and adaptation state agree to the last bit."""
+    from oracle.ref_port import replay_slice_port
+    t, meta, data = tapes(name)
+    model = BSModel(stan_file=meta["model"] + ".stan", data=data)
+    kw = {k: v for k, v in meta["ctor"].items() if k != "seed"}
+    n = min(400, len(t["e"]))
+    out = replay_slice_port(t, model, n=n, **kw)
+    assert np.array_equal(out["x1"], t["x1"][:n])
+    assert np.array_equal(out["n_shrink"], t["n_shrink"][:n])
+    assert np.array_equal(out["evals"], t["evals"][:n])
+    assert np.array_equal(out["theta"][:-1], t["theta0"][1:n])
+    s = out["sampler"]
+    k = int((t["closure_draw"] <= n).sum())
+    assert k >= 1
+    assert np.array_equal(s.dir_mean, t["closure_mean"][k - 1])
+    assert np.array_equal(s.dir_cov, t["closure_cov"][k - 1])
+    assert np.array_equal(s.eigvecs, t["closure_eigvecs"][k - 1])
+    assert np.array_equal(s.eigvals, t["closure_eigvals"][k - 1])
+
+
+@pytest.mark.parametrize("name", ["freerun_funnel_d2_slice_adapt", "freerun_illnormal_d20_slice_adapt"])
+def test_slice_port_reproduces_seeded_free_runs_of_the_reference(name):
+    import json
+    from conftest import GOLDEN
+    from oracle.ref_port import SliceChain
+    t = dict(np.load(GOLDEN / f"{name}.npz"))
+    meta, data = json.loads(str(t["meta_json"])), json.loads(str(t["data_json"]))
+    s = SliceChain(BSModel(stan_file=meta["model"] + ".stan", data=data), **meta["ctor"])
+    out = np.array([s.draw() for _ in range(meta["draws"])])
+    assert np.array_equal(out, t["thetas"])
+    assert float(s.acceptance_probability) == float(t["acceptance_probability"]) == 1.0
+
+
 def test_quadrature_table(tapes):
     # SURVEY.md 8c (3): values after the reference's normalisation, klhr.py:46-49
     from oracle.ref_port import gauss_hermite_probabilists

@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--tag", default="")
 ap.add_argument("--octet", action="store_true")
+ap.add_argument("--slice", action="store_true", help="time klhr_slice_run instead of klhr_run")
 ap.add_argument("--direction", action="store_true", help="eigen_method_one law: 2 mean columns + zero column")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -33,14 +34,19 @@ if a.direction:
     cols = torch.randn(2, D, dtype=torch.float64, device=dev).to(dt).contiguous()
     direction = kb.Direction(mean_cols=cols, sd=torch.ones(D, dtype=dt, device=dev),
                              cdf=torch.tensor([0.4, 0.7, 1.0], dtype=dt, device=dev), n_zero_cols=1)
-kb.run(model, fit, th, 50, 1, direction, accept_count=acc, evals_total=ev)
+if a.slice:
+    scfg = kb.SliceConfig()
+    _run = lambda n, off: kb.slice_run(model, scfg, th, n, 1, direction, draw_offset=off, accept_count=acc, evals_total=ev)
+else:
+    _run = lambda n, off: kb.run(model, fit, th, n, 1, direction, draw_offset=off, accept_count=acc, evals_total=ev)
+_run(50, 0)
 torch.cuda.synchronize()
 acc.zero_(); ev.zero_()
 times = []
 for r in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kb.run(model, fit, th, a.draws, 1, direction, draw_offset=50 + r * a.draws, accept_count=acc, evals_total=ev)
+    _run(a.draws, 50 + r * a.draws)
     e1.record()
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
