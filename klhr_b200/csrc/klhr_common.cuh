@@ -141,7 +141,7 @@ constexpr uint32_t kSlotInit4 = 3;     // w0..w3: two Box-Muller pairs -> init4[
 constexpr uint32_t kSlotDir = 8;       // direction element i: slot kSlotDir + (i % 8) + 8 ((i % 128) / 32) + 32 (i / 128), word (i % 32) / 8
 
 // uniform in (0,1) from 32 bits: (x + 0.5) / 2^32
-__device__ __forceinline__ float u01_32(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u01_32(uint32_t x) { return fmaf((float)(x >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f); }
 // uniform in (0,1) from 53 of 64 bits
 __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
@@ -154,8 +154,10 @@ __device__ __forceinline__ void box_muller_f32(uint32_t a, uint32_t b, float& z0
     const float u = u01_32(a);
     // -2 ln u = (-2 ln 2) lg2 u ; MUFU.LG2, MUFU.SQRT, MUFU.SIN/COS (approximate units are fine
     // for a direction law; the proposal normal uses box_muller_f64)
-    float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u)));
+    // u >= 2^-25 is never denormal: the .ftz forms skip the denormal fix-up __log2f would add
+    float lg, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg));
     const float ang = (float)b * 1.4629180792671596e-09f;       // 2 pi / 2^32 * b
     z0 = rad * __cosf(ang);
     z1 = rad * __sinf(ang);
