@@ -109,24 +109,21 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
     unsigned long long n_evals = 0;
 
     for (int step = 0; step < a.n_steps; ++step) {
-        constexpr bool last = false;                     // (the flush of pending moves is a separate loop below)
         const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
         const uint32_t d0 = (uint32_t)draw, k1d = k1 ^ (uint32_t)(draw >> 32);
         R u_col = 0, z_init = 0, z_prop = 0, u = 0;
         int jcol = 0;
-        if (!last) {
-            if constexpr (kReplay) {
-                if (own_valid) {
-                    z_init = reinterpret_cast<const R*>(a.z_init)[c_own];
-                    z_prop = reinterpret_cast<const R*>(a.z_prop)[c_own];
-                    u = reinterpret_cast<const R*>(a.u)[c_own];
-                }
-            } else {
-                const unsigned long long cid = (unsigned long long)(a.chain_offset + c_own);
-                chain_scalars<R>((uint32_t)cid, (uint32_t)(cid >> 32), d0, k0, k1d, u_col, z_init, z_prop, u);
-                if (n_cols > 1)                           // searchsorted(cdf, u, 'right'), klhr.py:147
-                    while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
+        if constexpr (kReplay) {
+            if (own_valid) {
+                z_init = reinterpret_cast<const R*>(a.z_init)[c_own];
+                z_prop = reinterpret_cast<const R*>(a.z_prop)[c_own];
+                u = reinterpret_cast<const R*>(a.u)[c_own];
             }
+        } else {
+            const unsigned long long cid = (unsigned long long)(a.chain_offset + c_own);
+            chain_scalars<R>((uint32_t)cid, (uint32_t)(cid >> 32), d0, k0, k1d, u_col, z_init, z_prop, u);
+            if (n_cols > 1)                               // searchsorted(cdf, u, 'right'), klhr.py:147
+                while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
         }
         R my_ss = 1, my_A = 0, my_B = 0;
         // -------------------------------------------------------------------- D-phase
@@ -171,15 +168,13 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                 // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
                 float z[8];
                 if constexpr (!kReplay) {
-                    if (!last) {
-                        uint32_t w[2][4];
-                        Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
-                                          k0, k1d, w);
+                    uint32_t w[2][4];
+                    Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
+                                      k0, k1d, w);
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
-                            box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
-                        }
+                    for (int t = 0; t < 2; ++t) {
+                        box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
+                        box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
                     }
                 }
                 // 3. apply the pending move, form the new x and the three sums
@@ -194,22 +189,20 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                             t0 = t0 + cp * (R)xo[s];
                             row[i] = t0;
                         }
-                        if (!last) {
-                            R x;
-                            if constexpr (kReplay) {
-                                x = reinterpret_cast<const R*>(a.rho)[c * D + i];
-                                xr[i] = (XT)x;
-                            } else {
-                                const float xf = fmaf(s_sd[i], z[s], has_mean ? mcol_s[i] : 0.0f);
-                                xr[i] = (XT)xf;
-                                x = (R)xf;
-                            }
-                            const R xt = x + tol;
-                            ss += xt * xt;
-                            const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
-                            sA += x * xw;
-                            sB += t0 * xw;
+                        R x;
+                        if constexpr (kReplay) {
+                            x = reinterpret_cast<const R*>(a.rho)[c * D + i];
+                            xr[i] = (XT)x;
+                        } else {
+                            const float xf = fmaf(s_sd[i], z[s], has_mean ? mcol_s[i] : 0.0f);
+                            xr[i] = (XT)xf;
+                            x = (R)xf;
                         }
+                        const R xt = x + tol;
+                        ss += xt * xt;
+                        const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
+                        sA += x * xw;
+                        sB += t0 * xw;
                     }
                 }
             };
@@ -227,13 +220,11 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                     }
                 }
             }
-            if (last) continue;
             ss = oct_sum(ss, om);
             sA = oct_sum(sA, om);
             sB = oct_sum(sB, om);
             if (j == p) { my_ss = ss; my_A = sA; my_B = sB; }
         }
-        if (last) break;
         // -------------------------------------------------------------------- fit phase (thread per chain)
         R inv = 1;
         if (own_valid) {
@@ -264,7 +255,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                 }
             }
             fit_and_propose<1, R, Model, 2>(cf, a.fp, 0, 0u, z_init, R(0), R(0), z_prop, u, so, oc);
-            if (!kReplay && oc.K > 0 && a.tr.or_r && true) {
+            if (!kReplay && oc.K > 0 && a.tr.or_r) {
                 a.tr.or_r[(long long)step * a.B + c_own] = oc.r;
                 reinterpret_cast<R*>(a.tr.or_v)[(long long)step * a.B + c_own] = oc.v;
             }
