@@ -25,7 +25,7 @@ constexpr int kThreadsMax = 256;
 #define KLHR_MIN_CTAS 3
 #endif
 template <typename R, typename Model>
-constexpr int step_min_ctas() { return (Model::kDenseCta && sizeof(R) == 8) ? 2 : KLHR_MIN_CTAS; }
+constexpr int step_min_ctas() { return (Model::kDenseCta && sizeof(R) == 8) ? (kDenseMaxChains > 16 ? 1 : 2) : KLHR_MIN_CTAS; }
 
 struct StepArgs {
     ModelParams mp;
@@ -379,7 +379,8 @@ struct LaunchPlan {
     size_t smem;
 };
 
-inline LaunchPlan plan_step(int D, int real_bytes, bool accum, int n_cols, bool replay, int max_threads = kThreadsMax) {
+inline LaunchPlan plan_step(int D, int real_bytes, bool accum, int n_cols, bool replay, int max_threads = kThreadsMax,
+                            size_t smem_target = 100 * 1024) {
     const int Dpad = pad_dim(D, real_bytes);
     LaunchPlan p;
     for (int threads = max_threads; threads >= 32; threads /= 2) {
@@ -388,8 +389,8 @@ inline LaunchPlan plan_step(int D, int real_bytes, bool accum, int n_cols, bool 
         const size_t tail = (size_t)D * (1 + (replay ? 0 : n_cols) + 1);
         p.threads = threads;
         p.smem = (rows * Dpad + tail) * real_bytes;
-        // aim for >= 2 CTAs per SM when possible
-        if (p.smem <= 100 * 1024 || threads == 32) break;
+        // default target: >= 2 CTAs per SM when possible
+        if (p.smem <= smem_target || threads == 32) break;
     }
     return p;
 }
@@ -399,8 +400,10 @@ int launch_step_typed(const StepArgs& args_in, int family, bool replay, bool acc
                       LaunchInfo* info) {
     StepArgs a = args_in;
     const int n_cols = a.dir.mean_cols ? a.dir.n_cols : 0;
-    const LaunchPlan p = plan_step(a.mp.D, (int)sizeof(R), accum, n_cols, replay,
-                                   (Model::kDenseCta && sizeof(R) == 8) ? 8 * kDenseMaxChains : kThreadsMax);
+    // dense DMMA path: as many chains per CTA as fit (every chain sharing the CTA reuses the P fragments)
+    constexpr bool dense = Model::kDenseCta && sizeof(R) == 8;
+    const LaunchPlan p = plan_step(a.mp.D, (int)sizeof(R), accum, n_cols, replay, dense ? 8 * kDenseMaxChains : kThreadsMax,
+                                   dense && kDenseMaxChains > 16 ? (size_t)200 * 1024 : (size_t)100 * 1024);
     if (p.smem > 227 * 1024) return -20;
     a.Dpad = pad_dim(a.mp.D, (int)sizeof(R));
     const void* fn = nullptr;
