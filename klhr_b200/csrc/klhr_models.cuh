@@ -169,7 +169,7 @@ struct Funnel {
         c.x0 = th[0];
         c.r0 = rh[0];
         c.hd = R(0.5) * (R)mp.i0;
-        c.l0 = -c.x0 * c.x0 / R(18) - c.hd * c.x0 - R(0.5) * r_exp(-c.x0) * c.a0;
+        c.l0 = -c.x0 * c.x0 * R(1.0 / 18.0) - c.hd * c.x0 - R(0.5) * r_exp(-c.x0) * c.a0;
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) {
@@ -178,9 +178,11 @@ struct Funnel {
         const R S = c.a0 + y * (R(2) * c.a1 + y * c.a2);
         const R S1 = R(2) * (c.a1 + y * c.a2);
         const R S2 = R(2) * c.a2;
-        const R l = -x * x / R(18) - c.hd * x - R(0.5) * ex * S - c.l0;
-        const R l1 = -c.r0 * x / R(9) - c.hd * c.r0 - R(0.5) * ex * (S1 - c.r0 * S);
-        const R l2 = -c.r0 * c.r0 / R(9) - R(0.5) * ex * (c.r0 * c.r0 * S - R(2) * c.r0 * S1 + S2);
+        // x^2 / 18 and friends as multiplications by the rounded reciprocal: an fp64 division costs ~20
+        // instructions and this runs once per quadrature node (1 ulp away from the oracle's division)
+        const R l = -x * x * R(1.0 / 18.0) - c.hd * x - R(0.5) * ex * S - c.l0;
+        const R l1 = -c.r0 * x * R(1.0 / 9.0) - c.hd * c.r0 - R(0.5) * ex * (S1 - c.r0 * S);
+        const R l2 = -c.r0 * c.r0 * R(1.0 / 9.0) - R(0.5) * ex * (c.r0 * c.r0 * S - R(2) * c.r0 * S1 + S2);
         return jet_guard<R>(l, l1, l2);
     }
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
