@@ -9,7 +9,8 @@ scripts, without the plots (matplotlib is not a dependency here).
 Flags and defaults are those of reference ``experiment_accuracy.py:14-25``, ``experiment_ar1.py:16-28``,
 ``experiment_funnel.py:15-26`` and ``experiment_relaxationtime.py:14-26``; ``ALGO`` is ``klhr``, ``klhr_sinh``,
 ``sub_klhr_sinh``, ``slice`` or (accuracy only, as the comparison arm) ``mh``.  Added: ``--chains`` (every metric is
-averaged over that many independent chains), ``--data`` (Stan JSON file), ``--seed``, ``--out`` (JSON file).
+averaged over that many independent chains), ``--data`` (Stan JSON file), ``--seed``, ``--out`` (JSON file),
+``--draws-out`` / ``--draws-chains`` (parquet dump of the draws, the output the reference left commented out).
 Each command prints one JSON object with the quantities the reference plots or prints under ``-v``
 (acceptance rate, MSJD, RMSE of running means / variances, posterior summaries, gradient evaluations).
 """
@@ -45,6 +46,9 @@ def common(fn):
         click.option("--data", type=click.Path(), default=None, help="Stan JSON data file"),
         click.option("--seed", type=int, default=None),
         click.option("--out", type=click.Path(), default=None, help="write the JSON summary here too"),
+        click.option("--draws-out", "draws_out", type=click.Path(), default=None,
+                     help="write the draws as parquet (one column per parameter, plus chain and iteration)"),
+        click.option("--draws-chains", "draws_chains", type=int, default=16, help="chains kept in --draws-out"),
         click.argument("algorithm", type=str),
     ]
     for o in reversed(opts):
@@ -84,6 +88,13 @@ def msjd(draws):
     return float((draws[1:] - draws[:-1]).double().norm(dim=-1).mean())
 
 
+def dump_draws(draws, model, kw):
+    """The parquet dump the reference scripts left commented out (experiment_ar1.py:93-94)."""
+    if kw.get("draws_out"):
+        from .output import write_draws
+        write_draws(kw["draws_out"], draws, model.parameter_names(), chains=kw["draws_chains"])
+
+
 def emit(summary, kw):
     text = json.dumps(summary)
     print(text)
@@ -116,6 +127,8 @@ def accuracy(**kw):
         draws = algo.sample(M)
         draws = draws if torch.is_tensor(draws) else torch.as_tensor(draws)[:, None, :]
         rm, rv = running_rmse(draws)
+        if name == kw["algorithm"]:
+            dump_draws(draws, model, kw)
         lp = model.log_density(draws[-1].to(model.device))
         out[name] = {"acceptance": algo.acceptance_probability, "msjd": msjd(draws),
                      "rmse_mean": {str(k): float(rm[k - 1]) for k in checkpoints(M)},
@@ -133,6 +146,7 @@ def ar1(**kw):
     algo = make_sampler(kw["algorithm"], model, kw)
     draws = algo.sample(kw["M"])
     draws = draws if torch.is_tensor(draws) else torch.as_tensor(draws)[:, None, :]
+    dump_draws(draws, model, kw)
     post = draws[kw["warmup"]:].double()
     v = post.var(0, unbiased=True)
     m = post.mean(0)
@@ -152,6 +166,7 @@ def funnel(**kw):
     algo = make_sampler(kw["algorithm"], model, kw)
     draws = algo.sample(kw["M"])
     draws = draws if torch.is_tensor(draws) else torch.as_tensor(draws)[:, None, :]
+    dump_draws(draws, model, kw)
     x = draws[kw["warmup"]:, :, 0].double().flatten()
     xs, _ = torch.sort(x)
     cdf = 0.5 * (1 + torch.erf(xs / (3 * math.sqrt(2))))
@@ -172,6 +187,7 @@ def relaxation(**kw):
     algo = make_sampler(kw["algorithm"], model, kw)
     draws = algo.sample(kw["M"])
     draws = draws if torch.is_tensor(draws) else torch.as_tensor(draws)[:, None, :]
+    dump_draws(draws, model, kw)
     M, B, D = draws.shape
     lp = model.log_density(draws.reshape(-1, D).to(model.device)).reshape(M, B).double()
     tail = lp[max(kw["warmup"], M // 2):]

@@ -24,8 +24,12 @@ def test_accuracy_experiment_klhr_beats_random_walk():
     assert k["msjd"] > 5 * m["msjd"]
 
 
-def test_ar1_and_funnel_experiments():
-    a = _run(["ar1", "-M", "600", "-w", "200", "--chains", "256", "--seed", "2", "-e1", "klhr"])
+def test_ar1_and_funnel_experiments(tmp_path):
+    a = _run(["ar1", "-M", "600", "-w", "200", "--chains", "256", "--seed", "2", "-e1", "--draws-out",
+              str(tmp_path / "ar1.parquet"), "--draws-chains", "3", "klhr"])
+    import pyarrow.parquet as pq
+    t = pq.read_table(tmp_path / "ar1.parquet")
+    assert t.num_rows == 600 * 3 and t.column_names[:3] == ["chain", "iteration", "y.1"] and t.num_columns == 102
     assert a["D"] == 100 and a["acceptance"] > 0.999 and a["max_abs_mean_pooled"] < 0.2
     f = _run(["funnel", "-M", "1500", "-w", "500", "--chains", "1024", "--seed", "3", "klhr_sinh"])
     assert abs(f["x_sd"] - 3.0) < 0.35 and abs(f["x_mean"]) < 0.3 and f["ks_distance_to_N(0,3)"] < 0.06

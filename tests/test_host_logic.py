@@ -135,3 +135,21 @@ def test_fit_config_validation():
     f = kb.FitConfig()
     assert np.isclose(f.w.sum(), 1) and f.descriptor().n_nodes == 8
     assert kb.FitConfig().for_dtype(torch.float32).gtol2 >= 1e-5
+
+
+def test_draws_parquet_round_trip(tmp_path):
+    """klhr_b200.output: the parquet layout the reference scripts intended (experiment_ar1.py:93-94)."""
+    import numpy as np
+    import pyarrow.parquet as pq
+    from klhr_b200.output import write_draws
+    rng = np.random.default_rng(0)
+    draws = rng.normal(size=(7, 5, 3))
+    n = write_draws(tmp_path / "d.parquet", draws, ["a", "b.1", "b.2"], chains=2, thin=3, first_iteration=1)
+    t = pq.read_table(tmp_path / "d.parquet").to_pandas()
+    assert n == 14 and list(t.columns) == ["chain", "iteration", "a", "b.1", "b.2"]
+    assert t["iteration"].tolist()[:4] == [1, 1, 4, 4] and t["chain"].tolist()[:4] == [0, 1, 0, 1]
+    assert np.array_equal(t[["a", "b.1", "b.2"]].to_numpy().reshape(7, 2, 3), draws[:, :2])
+    one = rng.normal(size=(4, 3))                      # a single chain, (M, D) like the reference
+    assert write_draws(tmp_path / "one.parquet", one, ["x", "y", "z"]) == 4
+    with __import__("pytest").raises(ValueError):
+        write_draws(tmp_path / "bad.parquet", draws, ["a"])
