@@ -202,6 +202,10 @@ int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int 
                       const void* rho_dev, const void* e_dev, const void* u0_dev, const void* shrink_u_dev,
                       const klhr_trace_t* trace, int64_t n_chains, void* stream);
 
+/* Test hook: y[i] = exp(x[i]) (op 0) or log(x[i]) (op 1) with the fp64 routines the fit kernels use
+ * (csrc/klhr_math.cuh), so their accuracy can be checked against the host math library. */
+int klhr_math_eval(int op, const double* x_dev, double* y_dev, int64_t n, void* stream);
+
 /* Pooled second-moment accumulation for the adaptation PCA (replaces the per-sample CCIPCA
  * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,
  * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype. */

@@ -431,6 +431,21 @@ int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int 
     return cuda_fail(dispatch_slice(a, dtype, true, (cudaStream_t)stream), "klhr_slice_replay");
 }
 
+// ---- elementwise fp64 exp / log of the fit's inner loops (klhr_math.cuh), exposed for the accuracy tests
+__global__ void math_kernel(int op, const double* __restrict__ x, double* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = op == 0 ? r_exp(x[i]) : r_log(x[i]);
+}
+
+int klhr_math_eval(int op, const double* x_dev, double* y_dev, int64_t n, void* stream) {
+    if (op != 0 && op != 1) return fail(-16, "klhr_math_eval: op must be 0 (exp) or 1 (log)");
+    if (n < 0) return fail(-10, "n must be non-negative");
+    if (n == 0) return 0;
+    if (!x_dev || !y_dev) return fail(-1, "x and y must not be NULL");
+    math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x_dev, y_dev, n);
+    return cuda_fail((int)cudaGetLastError(), "klhr_math_eval");
+}
+
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running, int accumulate,
                      int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* regs) {
     StepArgs a;

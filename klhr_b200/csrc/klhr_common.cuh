@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include "klhr_math.cuh"
+
 namespace klhr {
 
 constexpr int kOct = 8;                 // lanes per chain
@@ -47,7 +49,7 @@ template <> struct Num<float> {
     __device__ static __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
 };
 
-__device__ __forceinline__ double r_exp(double x) { return exp(x); }
+__device__ __forceinline__ double r_exp(double x) { return exp_c(x); }
 __device__ __forceinline__ float r_exp(float x) { return expf(x); }
 __device__ __forceinline__ double r_log(double x) { return log(x); }
 __device__ __forceinline__ float r_log(float x) { return logf(x); }
