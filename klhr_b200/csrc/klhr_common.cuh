@@ -51,7 +51,7 @@ template <> struct Num<float> {
 
 __device__ __forceinline__ double r_exp(double x) { return exp_c(x); }
 __device__ __forceinline__ float r_exp(float x) { return expf(x); }
-__device__ __forceinline__ double r_log(double x) { return log(x); }
+__device__ __forceinline__ double r_log(double x) { return log_c(x); }
 __device__ __forceinline__ float r_log(float x) { return logf(x); }
 __device__ __forceinline__ double r_log1p(double x) { return log1p(x); }
 __device__ __forceinline__ float r_log1p(float x) { return log1pf(x); }
