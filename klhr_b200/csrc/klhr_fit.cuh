@@ -27,6 +27,8 @@ struct FitParams {
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
 };
 
+constexpr double kNewtonCapD = 64.0;
+
 template <int G, typename R>
 __device__ __forceinline__ R grp_sum(R v, unsigned m) {
     if constexpr (G == kOct) return oct_sum(v, m);
@@ -34,6 +36,9 @@ __device__ __forceinline__ R grp_sum(R v, unsigned m) {
 }
 
 // ------------------------------------------------------------------ stage 1: 1-D mode search
+// A Newton step may be at most kNewtonCap trust radii long (oracle/batched.py:NEWTON_CAP): the candidates
+// step * 2^-k are scored by l, so a long step is only taken when it is the best point, and the exact Newton
+// step of a quadratic target gets through in ONE iteration at the posterior scales of the benchmark targets.
 template <int G, typename R, typename Model>
 __device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitParams& fp, int lane,
                             unsigned m, R& xi_out, R& tau0_out, int& nev) {
@@ -52,7 +57,7 @@ __device__ void stage1_mode(const typename Model::Coef& cf, R z_init, const FitP
         if (!__any_sync(wm, !done)) break;      // lock-step: finished chains idle, nobody serialises
         if (done) continue;
         const R newton = concave ? -J.l1 / J.l2 : R(0);
-        const R step = concave ? r_clamp(newton, -R(8) * trust, R(8) * trust) : r_clamp(J.l1, -trust, trust);
+        const R step = concave ? r_clamp(newton, -(R)kNewtonCapD * trust, (R)kNewtonCapD * trust) : r_clamp(J.l1, -trust, trust);
         nev += kOct;
         // the 8 candidates xi + 2^-k step: keep the arg-max of l, first maximum on ties
         R bv, bx, b1, b2;

@@ -13,7 +13,7 @@ a fixed iteration budget (``FitConfig``), the same one ``klhr_b200/csrc`` implem
 operation for operation:
 
   stage 1  1-D mode search on l(xi) = lp(theta + xi rho) from xi0 = z_init*initscale:
-           Newton step -l'/l'' where l'' < 0, otherwise a trust-capped ascent step; the 8
+           Newton step -l'/l'' (at most 64 trust radii) where l'' < 0, otherwise a trust-capped ascent step; the 8
            candidates xi + 2^-k step (k = 0..7) are scored and the best improving one kept.
   stage 2  Newton on the KL objective in scaled coordinates (m/s, log s[, log d, e]) with
            the exact Hessian (second directional derivative l'' of the target, analytic
@@ -110,6 +110,13 @@ def direction_mean(eigvecs, eigvals, method_one, family, uj=None):
 
 
 # ------------------------------------------------------------------ stage 1
+# stage 1: a Newton step may be at most this many trust radii long.  The candidates step * 2^-k are scored by
+# l, so a long step is only taken when it really is the best point; 64 lets the exact Newton step of a
+# quadratic target through at the posterior scales of the benchmark targets (ill-normal D = 100: |m*| up to
+# ~25), which a cap of 8 split into two iterations for almost every warp.
+NEWTON_CAP = 64.0
+
+
 def stage1_mode(model, theta, rho, z_init, cfg: FitConfig):
     """Returns (xi_hat, tau0, n_evals).  tau0 = 1/2 log(-1/l''(xi_hat)) when l'' < 0 else 0
     (reference ``klhr.py:133-134``: ``(s > 0) * 0.5 * log(s)`` with s = hess_inv)."""
@@ -130,7 +137,7 @@ def stage1_mode(model, theta, rho, z_init, cfg: FitConfig):
                 break
             newton = np.where(concave, -l1 / np.where(concave, l2, -1.0), 0.0)
             stepc = np.clip(l1, -trust, trust)
-            step = np.where(concave, np.clip(newton, -8.0 * trust, 8.0 * trust), stepc)
+            step = np.where(concave, np.clip(newton, -NEWTON_CAP * trust, NEWTON_CAP * trust), stepc)
         cand = xi[:, None] + step[:, None] * ks[None, :]
         cl, cl1, cl2 = line_eval(model, theta, rho, cand)
         nev += np.where(done, 0, 8)
