@@ -239,7 +239,7 @@ def run_b200(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     # ---------------------------------------------------------------- resident arm
-    clocks = ClockSampler(local) if rank == 0 and not os.environ.get("KLHR_BENCH_DIAG_NOCLOCKS") else None   # started early: nvidia-smi takes ~0.5 s to spin up
+    clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~0.5 s to spin up
     for _ in range(W):
         sampler.run(S)
     torch.cuda.synchronize()
@@ -249,8 +249,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     wall0 = time.time()
     for k in range(K):
-        if not os.environ.get("KLHR_BENCH_DIAG_NOFLUSH"):
-            flush.zero_()                      # L2 flush between timed iterations (state is 52 MB < L2)
+        flush.zero_()                          # L2 flush between timed iterations (state is 52 MB < L2)
         evs[k][0].record()
         sampler.run(S)                         # ONE klhr_run launch: B chains x S draws
         evs[k][1].record()
