@@ -135,69 +135,78 @@ static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, 
 }
 
 // ------------------------------------------------------------------ pooled outer products
-// outer[i][j] += sum_c (theta_ci - shift_i)(theta_cj - shift_j): a tall-skinny SYRK.  Each CTA
-// owns a 32x32 tile of the output and a slice of the chains; fp64 accumulation.
+// outer[i][j] += sum_c (theta_ci - shift_i)(theta_cj - shift_j): a tall-skinny SYRK on the FP64 tensor cores.
+// Each CTA owns a 32x32 tile of the output (upper triangle only) and a slice of the chains.  32 chains at a
+// time are staged in shared memory (shift subtracted, promoted to fp64); the tile is 4x4 m8n8 fragments: warp w
+// accumulates row fragment w / 2 against column fragments 2 (w % 2) and 2 (w % 2) + 1 with mma.sync.m8n8k4.f64,
+// three 64-bit shared loads per two DMMAs (row pitch 36 doubles: conflict-free fragment reads).
 template <typename R>
 __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta, const R* __restrict__ shift,
                                                     double* __restrict__ outer, double* __restrict__ s1,
                                                     long long B, int D, int chains_per_cta,
                                                     double* __restrict__ scratch) {
-    __shared__ double ta[32][33], tb[32][33];
+    constexpr int kPitch = 36;
+    __shared__ double ta[32][kPitch], tb[32][kPitch];
     const int ti = blockIdx.x * 32, tj = blockIdx.y * 32;
     if (tj < ti) return;                                 // upper triangle only; mirrored below
     const long long c_begin = (long long)blockIdx.z * chains_per_cta;
     const long long c_end = c_begin + chains_per_cta < B ? c_begin + chains_per_cta : B;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-    double acc[4] = {0, 0, 0, 0};
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 lanes x 8 warps
+    const int r8 = tx >> 2, k4 = tx & 3;                         // fragment coordinates
+    const int fm = ty >> 1, fn = 2 * (ty & 1);                   // row fragment, first of two column fragments
+    double acc[2][2] = {{0, 0}, {0, 0}};
     double colsum = 0;
+    const double sa = (shift && ti + tx < D) ? (double)shift[ti + tx] : 0.0;
+    const double sb = (shift && tj + tx < D) ? (double)shift[tj + tx] : 0.0;
     for (long long c0 = c_begin; c0 < c_end; c0 += 32) {
-        // load 32 chains x 32 dims for both tiles
+        // stage 32 chains x 32 dims of both tiles (rows of absent chains / dims are zero)
         for (int r = ty; r < 32; r += 8) {
             const long long c = c0 + r;
             const int ia = ti + tx, ib = tj + tx;
             double va = 0, vb = 0;
             if (c < c_end) {
-                if (ia < D) va = (double)theta[c * D + ia] - (shift ? (double)shift[ia] : 0.0);
-                if (ib < D) vb = (double)theta[c * D + ib] - (shift ? (double)shift[ib] : 0.0);
+                if (ia < D) va = (double)theta[c * D + ia] - sa;
+                if (ib < D) vb = (double)theta[c * D + ib] - sb;
             }
             ta[r][tx] = va;
             tb[r][tx] = vb;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const double b = tb[k][tx];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] += ta[k][ty + 8 * q] * b;
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            const double a = ta[k0 + k4][8 * fm + r8];           // A[i][k] = ta[k][i]
+            const double b0 = tb[k0 + k4][8 * fn + r8];          // B[k][j] = tb[k][j]
+            const double b1 = tb[k0 + k4][8 * fn + 8 + r8];
+            dmma_m8n8k4(acc[0][0], acc[0][1], a, b0);
+            dmma_m8n8k4(acc[1][0], acc[1][1], a, b1);
         }
         if (s1 && blockIdx.y == blockIdx.x && ty == 0)
             for (int k = 0; k < 32; ++k) colsum += ta[k][tx];
         __syncthreads();
     }
-    if (scratch) {
-        // deterministic mode: every chain slice writes its partial tile to its own scratch plane
-        // [slice][D*D + D]; outer_reduce_kernel adds the planes in a fixed order
-        double* plane = scratch + (size_t)blockIdx.z * ((size_t)D * D + D);
+    // C fragment: row r8, columns 2 k4 + {0, 1} of fragment (fm, fn + q)
+    double* plane = scratch ? scratch + (size_t)blockIdx.z * ((size_t)D * D + D) : nullptr;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int i = ti + ty + 8 * q, j = tj + tx;
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = ti + 8 * fm + r8, j = tj + 8 * (fn + q) + 2 * k4 + e;
             if (i < D && j < D) {
-                plane[(size_t)i * D + j] = acc[q];
-                if (ti != tj) plane[(size_t)j * D + i] = acc[q];
+                if (plane) {
+                    // deterministic mode: every chain slice writes its partial tile to its own scratch plane
+                    // [slice][D*D + D]; outer_reduce_kernel adds the planes in a fixed order
+                    plane[(size_t)i * D + j] = acc[q][e];
+                    if (ti != tj) plane[(size_t)j * D + i] = acc[q][e];
+                } else {
+                    atomicAdd(outer + (size_t)i * D + j, acc[q][e]);
+                    if (ti != tj) atomicAdd(outer + (size_t)j * D + i, acc[q][e]);
+                }
             }
         }
-        if (blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) plane[(size_t)D * D + ti + tx] = colsum;
-        return;
+    if (blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) {
+        if (plane) plane[(size_t)D * D + ti + tx] = colsum;
+        else if (s1) atomicAdd(s1 + ti + tx, colsum);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = ti + ty + 8 * q, j = tj + tx;
-        if (i < D && j < D) {
-            atomicAdd(outer + (size_t)i * D + j, acc[q]);
-            if (ti != tj) atomicAdd(outer + (size_t)j * D + i, acc[q]);
-        }
-    }
-    if (s1 && blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) atomicAdd(s1 + ti + tx, colsum);
 }
 
 __global__ void outer_reduce_kernel(const double* __restrict__ scratch, double* __restrict__ outer,
