@@ -202,6 +202,15 @@ int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int 
                       const void* rho_dev, const void* e_dev, const void* u0_dev, const void* shrink_u_dev,
                       const klhr_trace_t* trace, int64_t n_chains, void* stream);
 
+/* The reference's KL(eta, rho) (klhr.py:106-120 / klhr_sinh.py:163-176; the function its self-tests check
+ * against a numerical Jacobian, klhr.py:249-259, klhr_sinh.py:339-349) for every chain: theta [B][D], rho
+ * [B][D], eta [B][2|4] -> f [B], grad [B][2|4] in the reference's coordinates (m, log s[, log d, e]) and,
+ * if hess is not NULL, the Hessian [B][n][n] the Newton iteration uses (l'' of the target, second derivatives
+ * of the transport).  With KLHR_FIT_FIX_D the d row and column are those of the frozen parameter (0 / 1). */
+int klhr_kl_eval(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, const void* theta_dev,
+                 const void* rho_dev, const void* eta_dev, void* f_dev, void* grad_dev, void* hess_dev,
+                 int64_t n_chains, void* stream);
+
 /* Test hook: y[i] = exp(x[i]) (op 0) or log(x[i]) (op 1) with the fp64 routines the fit kernels use
  * (csrc/klhr_math.cuh), so their accuracy can be checked against the host math library. */
 int klhr_math_eval(int op, const double* x_dev, double* y_dev, int64_t n, void* stream);

@@ -79,6 +79,8 @@ EXPORTS = {
     "klhr_slice_replay": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SliceDesc), C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TraceDesc), C.c_int64,
                                     C.c_void_p]),
+    "klhr_kl_eval": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(FitDesc), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_math_eval": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_outer_accumulate": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

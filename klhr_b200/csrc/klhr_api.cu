@@ -440,6 +440,35 @@ int klhr_slice_replay(const klhr_model_t* model, const klhr_slice_t* slice, int 
     return cuda_fail(dispatch_slice(a, dtype, true, (cudaStream_t)stream), "klhr_slice_replay");
 }
 
+int klhr_kl_eval(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, const void* theta_dev,
+                 const void* rho_dev, const void* eta_dev, void* f_dev, void* grad_dev, void* hess_dev,
+                 int64_t n_chains, void* stream) {
+    KlArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (int e = check_model(model, a.mp)) return e;
+    if (int e = check_fit(fit, a.fp)) return e;
+    if (dtype != KLHR_F64 && dtype != KLHR_F32) return fail(-9, "dtype must be KLHR_F64 or KLHR_F32");
+    if (n_chains < 0) return fail(-10, "n_chains must be non-negative");
+    if (n_chains == 0) return 0;
+    if (!theta_dev || !rho_dev || !eta_dev || !f_dev || !grad_dev)
+        return fail(-1, "theta, rho, eta, f, grad must not be NULL");
+    a.theta = theta_dev; a.rho = rho_dev; a.eta = eta_dev; a.f = f_dev; a.grad = grad_dev; a.hess = hess_dev;
+    a.B = n_chains;
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = -2;
+    switch (a.mp.id) {
+        case KLHR_MODEL_NORMAL: e = launch_kl_normal(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_ILL_NORMAL: e = launch_kl_ill_normal(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_FUNNEL: e = launch_kl_funnel(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_CORR_NORMAL: e = launch_kl_corr_normal(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_AR1: e = launch_kl_ar1(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_ARK: e = launch_kl_ark(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_ROSENBROCK: e = launch_kl_rosenbrock(a, dtype, fit->family, st); break;
+        case KLHR_MODEL_EARNINGS: e = launch_kl_earnings(a, dtype, fit->family, st); break;
+    }
+    return cuda_fail(e, "klhr_kl_eval");
+}
+
 // ---- elementwise fp64 exp / log of the fit's inner loops (klhr_math.cuh), exposed for the accuracy tests
 __global__ void math_kernel(int op, const double* __restrict__ x, double* __restrict__ y, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -373,6 +373,92 @@ __global__ void __launch_bounds__(kThreadsMax) eval_kernel(ModelParams mp, const
         for (int i = lane; i < D; i += kOct) grad[c * D + i] = ok ? g[i] : R(0);
 }
 
+// ------------------------------------------------------------------ KL objective at a given eta
+// The reference's KL(eta, rho) (klhr.py:106-120, klhr_sinh.py:163-176) for every chain: value and gradient in
+// the reference's own coordinates (m, log s[, log d, e]) -- the fit works in m / s -- plus the Hessian the
+// Newton iteration uses.  lp(theta) is added back: the kernels work with l(y) - l(0).
+struct KlArgs {
+    ModelParams mp;
+    FitParams fp;
+    const void* theta;   // [B][D]
+    const void* rho;     // [B][D]
+    const void* eta;     // [B][NE]
+    void* f;             // [B]
+    void* grad;          // [B][NE]
+    void* hess;          // [B][NE][NE] or null
+    long long B;
+    int Dpad;
+};
+
+template <typename R, typename Model, int NE>
+__global__ void __launch_bounds__(kThreadsMax) kl_eval_kernel(const __grid_constant__ KlArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.mp.D, Dpad = a.Dpad;
+    const int cpb = blockDim.x / kOct;
+    const int o = threadIdx.x / kOct, lane = threadIdx.x & (kOct - 1);
+    const unsigned om = oct_mask();
+    R* sm = reinterpret_cast<R*>(smem_raw);
+    R* th = sm + (size_t)o * Dpad;
+    R* rh = sm + (size_t)(cpb + o) * Dpad;
+    const long long c = (long long)blockIdx.x * cpb + o;
+    if (c >= a.B) return;
+    for (int i = lane; i < D; i += kOct) {
+        th[i] = reinterpret_cast<const R*>(a.theta)[c * D + i];
+        rh[i] = reinterpret_cast<const R*>(a.rho)[c * D + i];
+    }
+    __syncwarp(om);
+    const typename Model::Coef cf = Model::setup(th, rh, lane, om, a.mp);
+    const R lp0 = Model::lp_grad(th, nullptr, lane, om, a.mp);
+    R eta[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) eta[k] = reinterpret_cast<const R*>(a.eta)[c * NE + k];
+    KLState<R, NE> S;
+    R s;
+    if constexpr (NE == 2) {
+        kl_gauss<kOct, R, Model>(cf, eta, a.fp, lane, om, S);
+        const R clip = (R)a.fp.scale_clip;
+        s = r_exp(r_clamp(eta[1], -clip, clip));
+    } else {
+        kl_sinh<kOct, R, Model>(cf, eta, a.fp, lane, om, S);
+        s = sinh_unpack<R>(eta, a.fp).s;
+    }
+    if (lane != 0) return;
+    const R is = R(1) / s;
+    reinterpret_cast<R*>(a.f)[c] = S.f - lp0;
+    R* g = reinterpret_cast<R*>(a.grad) + c * NE;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) g[k] = k == 0 ? S.g[0] * is : S.g[k];
+    if (a.hess) {
+        R* H = reinterpret_cast<R*>(a.hess) + c * NE * NE;
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+#pragma unroll
+            for (int j = 0; j < NE; ++j) H[i * NE + j] = S.H[i][j] * (i == 0 ? is : R(1)) * (j == 0 ? is : R(1));
+    }
+}
+
+template <typename R, typename Model>
+int launch_kl_typed(const KlArgs& args_in, int family, cudaStream_t st) {
+    KlArgs a = args_in;
+    a.Dpad = pad_dim(a.mp.D, (int)sizeof(R));
+    int threads = kThreadsMax;
+    size_t smem = 0;
+    for (; threads >= 32; threads /= 2) {
+        smem = (size_t)2 * (threads / kOct) * a.Dpad * sizeof(R);
+        if (smem <= 100 * 1024 || threads == 32) break;
+    }
+    if (smem > 227 * 1024) return -20;
+    const void* fn = family == KLHR_FAMILY_GAUSS ? (const void*)kl_eval_kernel<R, Model, 2>
+                                                 : (const void*)kl_eval_kernel<R, Model, 4>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int cpb = threads / kOct;
+    const long long grid = (a.B + cpb - 1) / cpb;
+    if (grid <= 0) return 0;
+    void* kargs[] = {(void*)&a};
+    return (int)cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), kargs, smem, st);
+}
+
 // ------------------------------------------------------------------ launch helpers
 struct LaunchPlan {
     int threads;
@@ -468,7 +554,8 @@ int launch_eval_typed(const ModelParams& mp, const void* theta, void* lp, void* 
     int launch_step_##name(const StepArgs& a, int dtype, int family, bool replay, bool accum,         \
                            cudaStream_t st, LaunchInfo* info);                                        \
     int launch_eval_##name(const ModelParams& mp, int dtype, const void* theta, void* lp, void* grad, \
-                           long long B, cudaStream_t st);
+                           long long B, cudaStream_t st);                                             \
+    int launch_kl_##name(const KlArgs& a, int dtype, int family, cudaStream_t st);
 
 #define KLHR_DEFINE_MODEL(name, M64, M32)                                                             \
     int launch_step_##name(const StepArgs& a, int dtype, int family, bool replay, bool accum,         \
@@ -480,6 +567,10 @@ int launch_eval_typed(const ModelParams& mp, const void* theta, void* lp, void* 
                            long long B, cudaStream_t st) {                                            \
         return dtype == KLHR_F64 ? launch_eval_typed<double, M64>(mp, theta, lp, grad, B, st)         \
                                  : launch_eval_typed<float, M32>(mp, theta, lp, grad, B, st);         \
+    }                                                                                                 \
+    int launch_kl_##name(const KlArgs& a, int dtype, int family, cudaStream_t st) {                   \
+        return dtype == KLHR_F64 ? launch_kl_typed<double, M64>(a, family, st)                        \
+                                 : launch_kl_typed<float, M32>(a, family, st);                        \
     }
 
 KLHR_DECLARE_MODEL(normal)

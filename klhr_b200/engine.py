@@ -157,6 +157,27 @@ def step_replay(model: BSModel, fit: FitConfig, theta, rho, z_init, z_prop, u, i
     return tr
 
 
+def kl_eval(model: BSModel, fit: FitConfig, theta, rho, eta, hessian=False):
+    """The reference's ``KL(eta, rho)`` (klhr.py:106-120 / klhr_sinh.py:163-176) for every chain: returns
+    ``(f (B,), grad (B, n))`` in the reference's coordinates, plus the Hessian ``(B, n, n)`` on request."""
+    lib = _lib.load()
+    for t, n in ((theta, "theta"), (rho, "rho"), (eta, "eta")):
+        _require_cuda(t, n)
+    B, D = theta.shape
+    if D != model.dim() or tuple(rho.shape) != (B, D) or tuple(eta.shape) != (B, fit.n_eta):
+        raise ValueError("kl_eval: theta (B, D), rho (B, D), eta (B, n_eta) expected")
+    dtype, dev = theta.dtype, theta.device
+    f = torch.empty(B, dtype=dtype, device=dev)
+    g = torch.empty(B, fit.n_eta, dtype=dtype, device=dev)
+    H = torch.empty(B, fit.n_eta, fit.n_eta, dtype=dtype, device=dev) if hessian else None
+    md, fd = model.descriptor(dtype, dev), fit.descriptor()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.klhr_kl_eval(C.byref(md), C.byref(fd), _dtype_code(dtype), theta.data_ptr(), rho.data_ptr(),
+                                    eta.data_ptr(), f.data_ptr(), g.data_ptr(), _ptr(H), B, st), "klhr_kl_eval")
+    return (f, g, H) if hessian else (f, g)
+
+
 @dataclass
 class Direction:
     """Device-resident direction law (reference ``_random_direction``, klhr.py:143-153)."""

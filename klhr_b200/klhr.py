@@ -266,6 +266,19 @@ class KLHR(MCMCBase):
         eta = tr.eta[0]
         return eta[0].double().cpu().numpy() if self.chains == 1 else eta
 
+    def KL(self, eta, rho):
+        """The KL objective and its gradient at ``eta`` along ``rho`` through the current state(s), like
+        reference ``KL`` (klhr.py:106-120 / klhr_sinh.py:163-176): ``(float, ndarray)`` for one chain,
+        ``(B,)`` / ``(B, n)`` tensors for a batch.  ``eta``: (n,) or (B, n); ``rho``: (D,) or (B, D)."""
+        f, g = engine.kl_eval(self.model, self._fit, self._theta, self._bcast(rho, self.D), self._bcast(eta, self._fit.n_eta))
+        if self.chains == 1:
+            return float(f[0]), g[0].double().cpu().numpy()
+        return f, g
+
+    def _bcast(self, v, n):
+        t = torch.as_tensor(np.asarray(v.detach().cpu() if torch.is_tensor(v) else v, dtype=np.float64)).reshape(-1, n)
+        return t.expand(self.chains, n).to(self.device, self.dtype).contiguous()
+
     def swap_state(self, theta):
         """Use ``theta`` (B, D) -- a contiguous device tensor of the sampler's dtype -- as the live chain
         state WITHOUT copying, e.g. to double-buffer host transfers against ``run``."""

@@ -18,3 +18,12 @@ class SUBKLHRSINH(KLHRSINH):
     def fit(self, rho, z_init=None):
         eta = super().fit(rho, z_init=z_init)
         return eta[..., [0, 1, 3]]
+
+    def KL(self, eta, rho):
+        """3-parameter ``KL`` (reference sub_klhr_sinh.py): eta = (m, log s, e)."""
+        import numpy as np
+        import torch
+        e = torch.as_tensor(np.asarray(eta.detach().cpu() if torch.is_tensor(eta) else eta, dtype=np.float64)).reshape(-1, 3)
+        e4 = torch.stack([e[:, 0], e[:, 1], torch.zeros_like(e[:, 0]), e[:, 2]], dim=1)
+        f, g = super().KL(e4, rho)
+        return f, g[..., [0, 1, 3]]
