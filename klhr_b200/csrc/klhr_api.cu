@@ -91,7 +91,7 @@ static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
     // the warp's x tile (32 x D fp32) must stay small enough for several one-warp CTAs per SM;
     // beyond D ~ 250 the octet kernel (theta resident in shared memory, fewer chains per CTA) takes over
     const bool small = (size_t)kTileChains * pad_dim(a.mp.D, 4) * 4 <= 32 * 1024;
-    return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && !a.acc.draws && small &&
+    return !(flags & KLHR_FIT_FORCE_OCTET) && family == KLHR_FAMILY_GAUSS && !accum && small &&
            (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) && n_stored <= 2;
 }
 

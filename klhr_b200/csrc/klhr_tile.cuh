@@ -63,7 +63,9 @@ __device__ __forceinline__ void chain_scalars(uint32_t c0, uint32_t c1, uint32_t
     u = sizeof(R) == 8 ? (R)u01_53(w[0], w[1]) : (R)u01_32(w[0]);
 }
 
-template <typename R, bool kScaled, typename XT, bool kReplay>
+// kDraws: thinned-draw output (MCMCBase.sample rows) -- a separate instantiation so that the plain run()
+// kernel carries none of it (the extra variants cost the hot path 6 % through register allocation otherwise)
+template <typename R, bool kScaled, typename XT, bool kReplay, bool kDraws>
 __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __grid_constant__ StepArgs a) {
     using Model = DiagNormal<R, kScaled>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
     const long long c_own = tile0 + 4 * j + o;           // the chain this thread owns in the fit phase
     const bool own_valid = j < kTilePasses && c_own < a.B;
     R* g_theta = reinterpret_cast<R*>(a.theta);
+    R* g_draws = kDraws ? reinterpret_cast<R*>(a.acc.draws) : nullptr;
     const R* g_w = reinterpret_cast<const R*>(a.mp.p0);
 
     if (KLHR_TILE_W_SMEM)
@@ -126,6 +129,11 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                 while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
         }
         R my_ss = 1, my_A = 0, my_B = 0;
+        // thinned output (MCMCBase.sample rows): the state after draw g = thin_offset + step (1-based) is
+        // formed on the fly in the D-phase of the NEXT draw, so that is where it is written
+        const long long g_prev = a.acc.thin_offset + step;
+        const bool emit_rt = kDraws && step > 0 && g_prev % a.acc.thin == 0;
+        const long long emit_row = emit_rt ? g_prev / a.acc.thin - 1 : 0;
         // -------------------------------------------------------------------- D-phase
         R cp_next = oct_bcast(c_pend, 0, om);
         int col_next = oct_bcast(jcol, 0, om);
@@ -145,14 +153,16 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
             const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
             const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
             const bool pend_rt = cp != R(0);
+            R* drow = emit_rt ? g_draws + ((emit_row * a.B + c) * D) : nullptr;
             R ss = 0, sA = 0, sB = 0;
             // Element i = g0 + j + 8 s, slot s = 4 t + r of this lane  <->  Philox counter slot
             // kSlotDir + j + 8 t + g0 / 4, word r.  A half handles slots 8h..8h+7 (blocks 2h, 2h+1).  When
             // the half is FULL (every slot live for every lane) the body carries no predicates at all;
             // only the last, partial half pays for bounds checks and skips its dead slots.
-            auto do_half = [&](auto full_tag, auto pend_tag, const int g0, const int h) {
+            auto do_half = [&](auto full_tag, auto pend_tag, auto emit_tag, const int g0, const int h) {
                 constexpr bool kFull = decltype(full_tag)::value;
                 constexpr bool pend = decltype(pend_tag)::value;   // a move of the previous draw is pending
+                constexpr bool emit = decltype(emit_tag)::value;   // the previous draw goes to the thinned output
                 // 1. issue the long-latency loads first (theta slice from L2, previous x); they hide
                 //    behind the RNG arithmetic of step 2.  Weights, scales and means are read from
                 //    shared memory at the point of use (preloading them needs > 128 registers).
@@ -189,6 +199,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                             t0 = t0 + cp * (R)xo[s];
                             row[i] = t0;
                         }
+                        if (emit) drow[i] = t0;           // the state after the previous draw (moved or not)
                         R x;
                         if constexpr (kReplay) {
                             x = reinterpret_cast<const R*>(a.rho)[c * D + i];
@@ -211,12 +222,24 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                 for (int h = 0; h < 2; ++h) {
                     if (g0 + 64 * h >= D) break;          // warp-uniform: nothing left
                     const bool full = g0 + 64 * h + 63 < D;
+                    if constexpr (kDraws) {
+                        if (emit_rt) {                    // warp-uniform (thinned sample() output)
+                            if (pend_rt) {
+                                if (full) do_half(std::true_type{}, std::true_type{}, std::true_type{}, g0, h);
+                                else do_half(std::false_type{}, std::true_type{}, std::true_type{}, g0, h);
+                            } else {
+                                if (full) do_half(std::true_type{}, std::false_type{}, std::true_type{}, g0, h);
+                                else do_half(std::false_type{}, std::false_type{}, std::true_type{}, g0, h);
+                            }
+                            continue;
+                        }
+                    }
                     if (pend_rt) {
-                        if (full) do_half(std::true_type{}, std::true_type{}, g0, h);
-                        else do_half(std::false_type{}, std::true_type{}, g0, h);
+                        if (full) do_half(std::true_type{}, std::true_type{}, std::false_type{}, g0, h);
+                        else do_half(std::false_type{}, std::true_type{}, std::false_type{}, g0, h);
                     } else {
-                        if (full) do_half(std::true_type{}, std::false_type{}, g0, h);
-                        else do_half(std::false_type{}, std::false_type{}, g0, h);
+                        if (full) do_half(std::true_type{}, std::false_type{}, std::false_type{}, g0, h);
+                        else do_half(std::false_type{}, std::false_type{}, std::false_type{}, g0, h);
                     }
                 }
             }
@@ -303,6 +326,19 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
         const XT* xr = xs + (size_t)cs * Dx;
         for (int i = j; i < D; i += kOct) row[i] = row[i] + cp * (R)xr[i];
     }
+    if constexpr (kDraws) {                               // the last draw of the launch, if it is a kept one
+        const long long g_last = a.acc.thin_offset + a.n_steps;
+        if (a.n_steps > 0 && g_last % a.acc.thin == 0) {
+            __syncwarp();
+            for (int p = 0; p < kTilePasses; ++p) {
+                const long long c = tile0 + 4 * p + o;
+                if (c >= a.B) continue;
+                const R* row = g_theta + c * D;
+                R* drow = g_draws + ((g_last / a.acc.thin - 1) * a.B + c) * D;
+                for (int i = j; i < D; i += kOct) drow[i] = row[i];
+            }
+        }
+    }
     if (own_valid) {
         if (a.acc.accept_count) a.acc.accept_count[c_own] += n_acc;
     }
@@ -325,8 +361,9 @@ int launch_tile_typed(const StepArgs& args_in, bool replay, cudaStream_t st, Lau
                   (size_t)(a.mp.D + n_cols) * sizeof(float);
     smem += (size_t)n_stored * a.mp.D * sizeof(float);
     if (smem > 227 * 1024) return -20;
-    const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true>
-                            : (const void*)tile_kernel<R, kScaled, float, false>;
+    const void* fn = replay ? (const void*)tile_kernel<R, kScaled, R, true, false>
+                            : (a.acc.draws ? (const void*)tile_kernel<R, kScaled, float, false, true>
+                                           : (const void*)tile_kernel<R, kScaled, float, false, false>);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     // one warp per CTA: ask for the largest shared-memory carve-out so that 14+ tiles fit per SM

@@ -489,3 +489,22 @@ def test_device_exp_log_accuracy():
     with np.errstate(all="ignore"):
         r = np.log(spl)
     assert np.array_equal(np.isnan(g), np.isnan(r)) and np.array_equal(g[~np.isnan(r)], r[~np.isnan(r)])
+
+
+def test_tile_kernel_thinned_draws_match_octet_kernel_and_states():
+    """sample(M, thin) on the tile kernel (pending moves applied on the fly): the rows are the chain states after
+    every thin-th draw -- equal to the octet kernel's rows up to round-off, across launch boundaries (adaptation
+    splits the run into launches of pca_stride draws) and for ragged batches."""
+    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": 100}, device=device())
+    for B, thin, M, warm in ((1000, 1, 25, 0), (333, 3, 12, 0), (257, 4, 20, 40)):
+        a = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
+        out_a = a.sample(M, thin=thin)
+        b = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
+        b._fit.force_octet = True
+        out_b = b.sample(M, thin=thin)
+        assert torch.allclose(out_a, out_b, rtol=1e-9, atol=1e-9)
+        assert torch.equal(out_a[-1], a.theta)                       # last row = live state
+        c = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
+        c.run((M - 1) * thin)
+        assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
+        assert float((out_a[1:] != out_a[:-1]).any(dim=2).float().mean()) > 0.9    # acceptance ~ 1: rows move
