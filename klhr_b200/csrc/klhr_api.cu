@@ -97,9 +97,9 @@ static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
 
 // The chain kernel (thread-per-chain fit, model-generic line setup) covers every target and both
 // families as long as its rho tile fits a modest shared-memory budget; like the tile kernel it
-// has no in-kernel accumulators and no thinned-draw output.
+// has no in-kernel accumulators (thinned draws are written by a second instantiation).
 static bool chain_applies(const StepArgs& a, int dtype, bool replay, bool accum, int flags) {
-    return !(flags & KLHR_FIT_FORCE_OCTET) && !accum && !a.acc.draws &&
+    return !(flags & KLHR_FIT_FORCE_OCTET) && !accum &&
            chain_smem_bytes(a, dtype == KLHR_F64 ? 8 : 4, replay) <= 20 * 1024;   // larger D: the octet kernel keeps theta resident
 }
 

@@ -20,7 +20,8 @@ namespace klhr {
 #define KLHR_CHAIN_MINCTAS 16   // 128 registers: the extra resident warps beat the small spills (measured, funnel)
 #endif
 
-template <typename R, typename Model, int NE, bool kReplay>
+// kDraws: thinned-draw output (MCMCBase.sample rows) as a separate instantiation, like the tile kernel
+template <typename R, typename Model, int NE, bool kReplay, bool kDraws>
 __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kPasses = 8;
@@ -93,6 +94,10 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
             }
         }
         typename Model::Coef my_cf;
+        // thinned output: the state after draw g = thin_offset + step (1-based) is staged at the top of the
+        // NEXT trip (the extra last trip covers the final draw), so that is where it is written
+        const long long g_prev = a.acc.thin_offset + step;
+        const bool emit_rt = kDraws && step > 0 && g_prev % a.acc.thin == 0;
         // -------------------------------------------------------------------- D-phase
 #pragma unroll 1
         for (int p = 0; p < kPasses; ++p) {
@@ -101,9 +106,12 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
             const R cp = oct_bcast(c_pend, p, om);
             const int col = oct_bcast(jcol, p, om);
             if (c >= a.B) continue;                       // octet-uniform
-            if (last && cp == R(0)) continue;
+            if (last && cp == R(0) && !emit_rt) continue;
             R* row = g_theta + c * D;
             R* rh = rho_all + (size_t)cs * Dp;
+            R* drow = nullptr;
+            if constexpr (kDraws)
+                if (emit_rt) drow = reinterpret_cast<R*>(a.acc.draws) + ((g_prev / a.acc.thin - 1) * a.B + c) * D;
             // theta row -> shared, with the pending move of the previous draw applied
             for (int i = j; i < D; i += kOct) {
                 R t0 = row[i];
@@ -112,6 +120,8 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
                     row[i] = t0;
                 }
                 th_s[i] = t0;
+                if constexpr (kDraws)
+                    if (drow) drow[i] = t0;
             }
             if (last) continue;
             if constexpr (kReplay) {
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
                 }
             }
             fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so, oc);
-            if (!kReplay && oc.K > 0 && a.tr.or_r && true) {
+            if (!kReplay && oc.K > 0 && a.tr.or_r) {
                 a.tr.or_r[(long long)step * a.B + c_own] = oc.r;
                 reinterpret_cast<R*>(a.tr.or_v)[(long long)step * a.B + c_own] = oc.v;
             }
@@ -231,10 +241,15 @@ int launch_chain_typed(const StepArgs& args_in, int family, bool replay, cudaStr
     const size_t smem = chain_smem_bytes(a, (int)sizeof(R), replay);
     if (smem > 227 * 1024) return -20;
     const void* fn;
+    const bool draws = !replay && a.acc.draws != nullptr;
     if (family == KLHR_FAMILY_GAUSS)
-        fn = replay ? (const void*)chain_kernel<R, Model, 2, true> : (const void*)chain_kernel<R, Model, 2, false>;
+        fn = replay ? (const void*)chain_kernel<R, Model, 2, true, false>
+                    : (draws ? (const void*)chain_kernel<R, Model, 2, false, true>
+                             : (const void*)chain_kernel<R, Model, 2, false, false>);
     else
-        fn = replay ? (const void*)chain_kernel<R, Model, 4, true> : (const void*)chain_kernel<R, Model, 4, false>;
+        fn = replay ? (const void*)chain_kernel<R, Model, 4, true, false>
+                    : (draws ? (const void*)chain_kernel<R, Model, 4, false, true>
+                             : (const void*)chain_kernel<R, Model, 4, false, false>);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (info) {

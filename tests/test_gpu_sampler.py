@@ -508,3 +508,22 @@ def test_tile_kernel_thinned_draws_match_octet_kernel_and_states():
         c.run((M - 1) * thin)
         assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
         assert float((out_a[1:] != out_a[:-1]).any(dim=2).float().mean()) > 0.9    # acceptance ~ 1: rows move
+
+
+@pytest.mark.parametrize("model_name,data,cls", [("funnel", {"D": 1}, "KLHRSINH"), ("funnel", {"D": 10}, "KLHR"),
+                                                 ("rosenbrock", {"D": 2}, "KLHR")])
+def test_chain_kernel_thinned_draws_match_octet_kernel(model_name, data, cls):
+    """sample(M, thin) on the chain kernel against the octet kernel's rows (same streams; fits that end on the
+    iteration budget may differ in the last bits, so a small fraction of chains is allowed to deviate)."""
+    model = kb.BSModel(stan_file=f"stan/{model_name}.stan", data=data, device=device())
+    for B, thin, M, warm in ((777, 1, 9, 0), (300, 3, 8, 30)):
+        mk = lambda: getattr(kb, cls)(model, seed=4, chains=B, warmup=warm, windowsize=10, overrelaxed=False)
+        a, b = mk(), mk()
+        b._fit.force_octet = True
+        out_a, out_b = a.sample(M, thin=thin), b.sample(M, thin=thin)
+        assert torch.equal(out_a[-1], a.theta)
+        same = torch.isclose(out_a, out_b, rtol=1e-8, atol=1e-8).all(dim=2).all(dim=0)      # per chain
+        assert float(same.double().mean()) >= 0.97, float(same.double().mean())
+        c = mk()
+        c.run((M - 1) * thin)
+        assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
