@@ -77,7 +77,9 @@ typedef struct klhr_fit {
     double initscale;            /* klhr.py:24                                            */
     double tol;                  /* klhr.py:28 / klhr_sinh.py:26                          */
     double scale_clip;           /* klhr.py:30 / klhr_sinh.py:28                          */
-    double gtol1, gtol2;         /* convergence thresholds of the two stages             */
+    double gtol1, gtol2;         /* convergence thresholds of the two stages: |l'|/sqrt(-l'') of the 1-D mode
+                                    search (1e-4: it only supplies the start of stage 2) and the inf-norm of the
+                                    scaled KL gradient (1e-10)                                              */
     double step_cap, c1, basin;  /* Newton step cap, Armijo constant, full-step basin     */
     double x[KLHR_MAX_NODES];    /* nodes  hermgauss(N).x * sqrt(2)   (klhr.py:46-48)      */
     double w[KLHR_MAX_NODES];    /* weights hermgauss(N).w / sqrt(pi) (klhr.py:49)         */

@@ -46,7 +46,7 @@ class FitConfig:
     nb: int = 8                      # back-tracking halvings per Newton step
     kmax: int = 0                    # cap on stage-2 KL evaluations per fit (0: 1 + n2 * nb)
     fix_d: bool = False              # sinh family with d = 1 frozen (reference sub_klhr_sinh.py)
-    gtol1: float = 1e-8              # |l'| / sqrt(-l'') at the mode
+    gtol1: float = 1e-4              # |l'| / sqrt(-l'') at the mode: stage 1 only supplies the START of stage 2
     gtol2: float = 1e-10             # inf-norm of the scaled KL gradient
     step_cap: float = 2.0            # inf-norm cap of a stage-2 step in scaled coordinates
     c1: float = 1e-4                 # Armijo constant (SciPy's c1, _optimize.py:1156)
