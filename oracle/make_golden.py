@@ -244,6 +244,11 @@ CASES = [
     ("rosenbrock_d4_sinh", "rosenbrock", {"D": 2}, "sinh", 1_000, dict(seed=72, overrelaxed=False), None),
     ("normal_d2_klhr_method2", "normal", {"D": 2}, "gauss", 1_500,
      dict(seed=81, eigen_method_one=False), None),
+    # direction covariance scaled by the gradient variances (klhr.py:205-206) and the method-two direction mean
+    ("illnormal_d20_klhr_scaledir", "ill-normal", {"D": 20}, "gauss", 260,
+     dict(seed=131, warmup=200, scale_dir_cov=True), None),
+    ("funnel_d2_sinh_scaledir_method1", "funnel", {"D": 1}, "sinh", 160,
+     dict(seed=132, warmup=100, scale_dir_cov=True, eigen_method_one=True, overrelaxed=False), None),
     # 3-parameter sinh-arcsinh variant (reference sub_klhr_sinh.py)
     ("funnel_d2_subsinh_tight", "funnel", {"D": 1}, "subsinh", 1_000, dict(seed=111, overrelaxed=False), 1e-9),
     ("rosenbrock_d4_subsinh", "rosenbrock", {"D": 2}, "subsinh", 400, dict(seed=112, overrelaxed=False), None),

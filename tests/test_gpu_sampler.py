@@ -527,3 +527,38 @@ def test_chain_kernel_thinned_draws_match_octet_kernel(model_name, data, cls):
         c = mk()
         c.run((M - 1) * thin)
         assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
+
+
+def test_adaptation_variants_scale_dir_cov_and_method_two():
+    """The constructor switches of the direction law (klhr.py:143-153,202-210): ``scale_dir_cov`` divides the
+    window variances by the variances of the model gradient, ``eigen_method_one=False`` uses one mean vector
+    (sum of eigenvalue-weighted eigenvectors; normalised weights in KLHRSINH, klhr_sinh.py:210).  The device state
+    must be what the host formulas say, and the posterior stays right under every law."""
+    D = 12
+    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": D}, device=device())
+    truth = np.arange(1, D + 1) ** 2 / D
+    for cls, kw in ((kb.KLHR, dict(scale_dir_cov=True)), (kb.KLHR, dict(eigen_method_one=False)),
+                    (kb.KLHRSINH, dict(scale_dir_cov=True, overrelaxed=False))):
+        s = cls(model, seed=6, chains=2048, warmup=400, windowsize=50, **kw)
+        s.run(400)
+        d = s._direction
+        assert np.allclose(d.sd.cpu().numpy() ** 2, s._cov, rtol=1e-12)
+        if kw.get("scale_dir_cov"):
+            # var(theta_i) / (tol + var(grad_i)) with grad_i = -theta_i / s_i^2  ->  ~ s_i^4 = truth^2
+            assert np.allclose(s._cov, truth ** 2, rtol=0.35), (s._cov, truth ** 2)
+        else:
+            assert np.allclose(s._cov, truth, rtol=0.3)
+        if s._eigen_method_one:
+            assert d.mean_cols.shape == (s.J, D) and d.n_zero_cols == 1
+            p = s._eigvals / s._eigvals.sum()
+            assert np.allclose(d.cdf.cpu().numpy(), np.cumsum(p) / np.cumsum(p)[-1], rtol=1e-12)
+        else:
+            lam = s._eigvals
+            wgt = lam / lam.sum() if cls is kb.KLHRSINH else lam
+            assert d.mean_cols.shape == (1, D) and d.cdf is None
+            assert np.allclose(d.mean_cols[0].cpu().numpy(), (wgt * s._eigvecs).sum(1), rtol=1e-12, atol=1e-12)
+        s1, s2 = s.run(1200, chain_stats=True)
+        summ = chain_summary(s1, s2, 1200)
+        z = np.abs(summ["mean"].cpu().numpy()) / summ["mcse_mean"].cpu().numpy()
+        zv = np.abs(summ["var"].cpu().numpy() - truth) / summ["mcse_var"].cpu().numpy()
+        assert z.max() <= 4.5 and zv.max() <= 4.5, (cls.__name__, kw, z.max(), zv.max())

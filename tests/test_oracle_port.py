@@ -8,7 +8,8 @@ from oracle.ref_port import replay_port
 
 CASES = [("normal_d2_klhr", 1100), ("normal_d2_klhr_method2", 400), ("illnormal_d100_klhr", 220),
          ("funnel_d2_klhr", 200), ("funnel_d2_sinh", 60), ("corrnormal_n50_klhr", 210),
-         ("ar1_n100_klhr", 60), ("ark_t200_sinh", 40), ("rosenbrock_d4_sinh", 40), ("rosenbrock_d4_subsinh", 60)]
+         ("ar1_n100_klhr", 60), ("ark_t200_sinh", 40), ("rosenbrock_d4_sinh", 40), ("rosenbrock_d4_subsinh", 60),
+         ("illnormal_d20_klhr_scaledir", 260), ("funnel_d2_sinh_scaledir_method1", 160)]
 
 
 @pytest.mark.parametrize("name,n", CASES)
