@@ -219,6 +219,9 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # started first: nvidia-smi can take a second to spin up on a fresh box, and only samples stamped inside the
+    # timed region are used
+    clocks = ClockSampler(local) if rank == 0 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -239,7 +242,6 @@ def run_b200(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     # ---------------------------------------------------------------- resident arm
-    clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~0.5 s to spin up
     for _ in range(W):
         sampler.run(S)
     torch.cuda.synchronize()
