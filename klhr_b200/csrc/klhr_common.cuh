@@ -56,6 +56,8 @@ __device__ __forceinline__ float r_log(float x) { return logf(x); }
 __device__ __forceinline__ double r_log1p(double x) { return log1p(x); }
 __device__ __forceinline__ float r_log1p(float x) { return log1pf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double r_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float r_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double r_abs(double x) { return fabs(x); }
 __device__ __forceinline__ float r_abs(float x) { return fabsf(x); }

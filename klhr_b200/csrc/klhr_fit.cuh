@@ -523,7 +523,8 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
         zp = eta[0] + s * z_prop;                   // klhr.py:180
         // _logq(0) - _logq(zp) (klhr.py:155-158,185-186): the two -log(s) terms cancel, so only
         // the quadratic parts are formed (saves two logs and two exps per draw)
-        const R z0 = (R(0) - eta[0]) / s, z1 = (zp - eta[0]) / s;
+        const R is = R(1) / s;                      // one division for both standardised points
+        const R z0 = (R(0) - eta[0]) * is, z1 = (zp - eta[0]) * is;
         lq0 = -R(0.5) * z0 * z0;
         lq1 = -R(0.5) * z1 * z1;
     } else {

@@ -31,9 +31,17 @@ struct ModelParams {
 template <typename R>
 struct QuadCoef { R A, Bq; };          // l(y) - l(0) = Bq y - A y^2 / 2
 
+// For a quadratic a finite l implies finite y, A and Bq (0 * inf and inf - inf are NaN), hence finite l' and
+// l'': one finiteness test gives the same (-inf, 0, 0) rule as the three of jet_guard.
 template <typename R>
 __device__ __forceinline__ Jet<R> quad_eval(const QuadCoef<R>& c, R y) {
-    return jet_guard<R>(y * (c.Bq - R(0.5) * c.A * y), c.Bq - c.A * y, -c.A);
+    const R l = y * (c.Bq - R(0.5) * c.A * y);
+    const bool ok = r_finite(l);
+    Jet<R> j;
+    j.l = ok ? l : -Num<R>::inf();
+    j.l1 = ok ? c.Bq - c.A * y : R(0);
+    j.l2 = ok ? -c.A : R(0);
+    return j;
 }
 
 // ---- stan/normal.stan:1-9 and stan/ill-normal.stan:1-12  (diagonal Gaussian)

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
                 cf.A = my_A;
                 cf.Bq = -my_B;
             } else {
-                inv = R(1) / r_sqrt(my_ss);               // rho = x / ||x + tol||  (klhr.py:153)
+                inv = r_rsqrt(my_ss);                     // rho = x / ||x + tol||  (klhr.py:153)
                 cf.A = my_A * inv * inv;
                 cf.Bq = -my_B * inv;
             }
