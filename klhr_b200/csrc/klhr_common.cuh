@@ -167,12 +167,9 @@ __device__ __forceinline__ void box_muller_f32(uint32_t a, uint32_t b, float& z0
     z1 = rad * __sinf(ang);
 }
 
-__device__ __forceinline__ void box_muller_f64(double u, double v, double& z0, double& z1) {
-    const double rad = sqrt(-2.0 * log(u));
-    double s, c;
-    sincospi(2.0 * v, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+// One fp64 normal from two 53-bit uniforms (the proposal variate): only the cosine branch is ever used
+__device__ __forceinline__ double box_muller_f64(double u, double v) {
+    return sqrt(-2.0 * log_c(u)) * cospi(2.0 * v);
 }
 
 }  // namespace klhr

@@ -108,6 +108,7 @@ struct KLState {
     R f;
     R g[n];
     R H[n][n];          // full symmetric storage (n = 2 or 4)
+    R s;                // the family's scale at the evaluated eta (saves recomputing exp(eta_1) for the proposal)
 };
 
 // Solve (H) p = -g by Cholesky, entry by entry like oracle/batched.py:_chol_solve.
@@ -215,6 +216,7 @@ __device__ void kl_gauss(const typename Model::Coef& cf, const R (&eta)[2], cons
     S0 = grp_sum<G>(S0, m); S1 = grp_sum<G>(S1, m); S1x = grp_sum<G>(S1x, m);
     S2 = grp_sum<G>(S2, m); S2x = grp_sum<G>(S2x, m); S2xx = grp_sum<G>(S2xx, m);
     const R s2 = s * s;
+    S.s = s;
     S.f = -(S0 + eta[1]);
     S.g[0] = -S1 * s;
     S.g[1] = -(S1x * s + R(1));
@@ -295,6 +297,7 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         g2 = 0; h02 = 0; h12 = 0; h23 = 0; h22 = 1;
     }
     const R s = q.s;
+    S.s = s;
     S.g[0] = g0 * s; S.g[1] = g1; S.g[2] = g2; S.g[3] = g3;
     S.H[0][0] = h00 * s * s;
     S.H[0][1] = S.H[1][0] = h01 * s;
@@ -327,7 +330,7 @@ __device__ __forceinline__ R scale_of(const R (&eta)[n], const FitParams& fp) {
 // with 4 octets (or 32 single-thread chains) per warp the nested form ran one group at a time.
 template <int G, typename R, typename Model, int n>
 __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
-                              unsigned m, int& nev, bool& converged) {
+                              unsigned m, int& nev, bool& converged, R& s_out) {
     const unsigned wm = __activemask();        // the lanes that entered together stay in lock-step
     KLState<R, n> S;
     R p[n], trial[n];
@@ -400,6 +403,7 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
         }
     }
     converged = conv;
+    s_out = S.s;               // scale at the returned eta (the last accepted evaluation)
 }
 
 // ------------------------------------------------------------------ family densities / transport
@@ -507,11 +511,11 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
         }
     }
     bool conv;
-    stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv);
+    R s_fit;
+    stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv, s_fit);
     R zp, lq0, lq1;
     if constexpr (n == 2) {
-        const R c = (R)fp.scale_clip;
-        const R s = r_exp(r_clamp(eta[1], -c, c));
+        const R s = s_fit;                          // = exp(clamp(eta[1])), klhr.py:81-85
         if (oc.K > 0) {                             // klhr.py:160-173
             const R u0 = r_normcdf((R(0) - eta[0]) / s);
             if (!oc.inject) overrelax_sample<R>(oc, u0);

@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(kThreadsMax, step_min_ctas<R, Model>()) step_k
                         sv1 = (R)z0;
                     } else if ((lane & 3) == 1) {     // slot 1: z_prop
                         if (sizeof(R) == 8) {
-                            double z0, z1;
-                            box_muller_f64(u01_53(w[0], w[1]), u01_53(w[2], w[3]), z0, z1);
+                            const double z0 = box_muller_f64(u01_53(w[0], w[1]), u01_53(w[2], w[3]));
                             sv0 = (R)z0;
                         } else {
                             float z0, z1;

@@ -52,8 +52,7 @@ __device__ __forceinline__ void chain_scalars(uint32_t c0, uint32_t c1, uint32_t
     z_init = (R)f0;
     Philox::block(c0, c1, d0, kSlotProposal, k0, k1d, w);
     if (sizeof(R) == 8) {
-        double z0, z1;
-        box_muller_f64(u01_53(w[0], w[1]), u01_53(w[2], w[3]), z0, z1);
+        const double z0 = box_muller_f64(u01_53(w[0], w[1]), u01_53(w[2], w[3]));
         z_prop = (R)z0;
     } else {
         box_muller_f32(w[0], w[2], f0, f1);
