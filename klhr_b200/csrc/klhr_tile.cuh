@@ -40,6 +40,19 @@ constexpr int kTilePasses = KLHR_TILE_PASSES;
 constexpr int kTileChains = 4 * kTilePasses;
 constexpr int kWarp = 32;
 
+// Octet shuffles with the FULL-warp mask: the whole warp reaches them together in the tile kernel, and a constant
+// full mask spares the MATCH / REDUX / BRA.DIV preamble the compiler emits for a per-octet mask (5 % of the
+// kernel's stall samples).
+template <typename R>
+__device__ __forceinline__ R warp_oct_sum(R v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+template <typename R>
+__device__ __forceinline__ R warp_oct_bcast(R v, int src) { return __shfl_sync(0xffffffffu, v, src, kOct); }
+
 // per-draw scalar variates of one chain (slots 0..2), computed by the owning thread
 template <typename R>
 __device__ __forceinline__ void chain_scalars(uint32_t c0, uint32_t c1, uint32_t d0, uint32_t k0, uint32_t k1d,
@@ -134,118 +147,119 @@ __global__ void __launch_bounds__(kWarp, KLHR_TILE_MINCTAS) tile_kernel(const __
         const bool emit_rt = kDraws && step > 0 && g_prev % a.acc.thin == 0;
         const long long emit_row = emit_rt ? g_prev / a.acc.thin - 1 : 0;
         // -------------------------------------------------------------------- D-phase
-        R cp_next = oct_bcast(c_pend, 0, om);
-        int col_next = oct_bcast(jcol, 0, om);
+        R cp_next = warp_oct_bcast(c_pend, 0);
+        int col_next = warp_oct_bcast(jcol, 0);
 #pragma unroll 1
         for (int p = 0; p < kTilePasses; ++p) {
             const int cs = 4 * p + o;
             const long long c = tile0 + cs;
             const R cp = cp_next;                          // pending move of this pass's chain
             const int col = col_next;
-            cp_next = oct_bcast(c_pend, (p + 1) % kTilePasses, om);  // one pass ahead: hides the shuffle latency
-            col_next = oct_bcast(jcol, (p + 1) % kTilePasses, om);
-            if (c >= a.B) continue;                       // octet-uniform
-            R* row = g_theta + c * D;
-            XT* xr = xs + (size_t)cs * Dx;
-            const bool has_mean = col < n_stored;         // a zero column (klhr.py:64-66) is not stored
-            const float* mcol_s = s_mean + (size_t)(has_mean ? col : 0) * D;
-            const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
-            const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
-            const bool pend_rt = cp != R(0);
-            R* drow = emit_rt ? g_draws + ((emit_row * a.B + c) * D) : nullptr;
+            cp_next = warp_oct_bcast(c_pend, (p + 1) % kTilePasses);  // one pass ahead: hides the shuffle latency
+            col_next = warp_oct_bcast(jcol, (p + 1) % kTilePasses);
             R ss = 0, sA = 0, sB = 0;
-            // Element i = g0 + j + 8 s, slot s = 4 t + r of this lane  <->  Philox counter slot
-            // kSlotDir + j + 8 t + g0 / 4, word r.  A half handles slots 8h..8h+7 (blocks 2h, 2h+1).  When
-            // the half is FULL (every slot live for every lane) the body carries no predicates at all;
-            // only the last, partial half pays for bounds checks and skips its dead slots.
-            auto do_half = [&](auto full_tag, auto pend_tag, auto emit_tag, const int g0, const int h) {
-                constexpr bool kFull = decltype(full_tag)::value;
-                constexpr bool pend = decltype(pend_tag)::value;   // a move of the previous draw is pending
-                constexpr bool emit = decltype(emit_tag)::value;   // the previous draw goes to the thinned output
-                // 1. issue the long-latency loads first (theta slice from L2, previous x); they hide
-                //    behind the RNG arithmetic of step 2.  Weights, scales and means are read from
-                //    shared memory at the point of use (preloading them needs > 128 registers).
-                R th[8];
-                XT xo[8];
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int i = g0 + j + 8 * (8 * h + s);
-                    const bool live = kFull || i < D;
-                    th[s] = live ? row[i] : R(0);
-                    xo[s] = (pend && live) ? xr[i] : XT(0);
-                }
-                // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
-                float z[8];
-                if constexpr (!kReplay) {
-                    uint32_t w[2][4];
-                    Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
-                                      k0, k1d, w);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
-                        box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
+            if (c < a.B) {                                // octet-uniform; absent chains contribute zeros
+                R* row = g_theta + c * D;
+                XT* xr = xs + (size_t)cs * Dx;
+                const bool has_mean = col < n_stored;         // a zero column (klhr.py:64-66) is not stored
+                const float* mcol_s = s_mean + (size_t)(has_mean ? col : 0) * D;
+                const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
+                const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
+                const bool pend_rt = cp != R(0);
+                R* drow = emit_rt ? g_draws + ((emit_row * a.B + c) * D) : nullptr;
+                // Element i = g0 + j + 8 s, slot s = 4 t + r of this lane  <->  Philox counter slot
+                // kSlotDir + j + 8 t + g0 / 4, word r.  A half handles slots 8h..8h+7 (blocks 2h, 2h+1).  When
+                // the half is FULL (every slot live for every lane) the body carries no predicates at all;
+                // only the last, partial half pays for bounds checks and skips its dead slots.
+                auto do_half = [&](auto full_tag, auto pend_tag, auto emit_tag, const int g0, const int h) {
+                    constexpr bool kFull = decltype(full_tag)::value;
+                    constexpr bool pend = decltype(pend_tag)::value;   // a move of the previous draw is pending
+                    constexpr bool emit = decltype(emit_tag)::value;   // the previous draw goes to the thinned output
+                    // 1. issue the long-latency loads first (theta slice from L2, previous x); they hide
+                    //    behind the RNG arithmetic of step 2.  Weights, scales and means are read from
+                    //    shared memory at the point of use (preloading them needs > 128 registers).
+                    R th[8];
+                    XT xo[8];
+    #pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int i = g0 + j + 8 * (8 * h + s);
+                        const bool live = kFull || i < D;
+                        th[s] = live ? row[i] : R(0);
+                        xo[s] = (pend && live) ? xr[i] : XT(0);
                     }
-                }
-                // 3. apply the pending move, form the new x and the three sums
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int ib = g0 + 8 * (8 * h + s);
-                    if (!kFull && ib >= D) continue;      // warp-uniform: dead slot of the partial half
-                    const int i = ib + j;
-                    if (kFull || i < D) {
-                        R t0 = th[s];
-                        if (pend) {
-                            t0 = t0 + cp * (R)xo[s];
-                            row[i] = t0;
+                    // 2. 8 normals: two Philox blocks advanced in lockstep, four Box-Muller pairs
+                    float z[8];
+                    if constexpr (!kReplay) {
+                        uint32_t w[2][4];
+                        Philox::blockN<2>(c0, c1, d0, kSlotDir + (uint32_t)(j + 16 * h) + (uint32_t)(g0 / 4), 8u,
+                                          k0, k1d, w);
+    #pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            box_muller_f32(w[t][0], w[t][1], z[4 * t + 0], z[4 * t + 1]);
+                            box_muller_f32(w[t][2], w[t][3], z[4 * t + 2], z[4 * t + 3]);
                         }
-                        if (emit) drow[i] = t0;           // the state after the previous draw (moved or not)
-                        R x;
-                        if constexpr (kReplay) {
-                            x = reinterpret_cast<const R*>(a.rho)[c * D + i];
-                            xr[i] = (XT)x;
-                        } else {
-                            const float xf = fmaf(s_sd[i], z[s], has_mean ? mcol_s[i] : 0.0f);
-                            xr[i] = (XT)xf;
-                            x = (R)xf;
-                        }
-                        const R xt = x + tol;
-                        ss += xt * xt;
-                        const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
-                        sA += x * xw;
-                        sB += t0 * xw;
                     }
-                }
-            };
-            for (int g0 = 0; g0 < D; g0 += 128) {
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    if (g0 + 64 * h >= D) break;          // warp-uniform: nothing left
-                    const bool full = g0 + 64 * h + 63 < D;
-                    if constexpr (kDraws) {
-                        if (emit_rt) {                    // warp-uniform (thinned sample() output)
-                            if (pend_rt) {
-                                if (full) do_half(std::true_type{}, std::true_type{}, std::true_type{}, g0, h);
-                                else do_half(std::false_type{}, std::true_type{}, std::true_type{}, g0, h);
-                            } else {
-                                if (full) do_half(std::true_type{}, std::false_type{}, std::true_type{}, g0, h);
-                                else do_half(std::false_type{}, std::false_type{}, std::true_type{}, g0, h);
+                    // 3. apply the pending move, form the new x and the three sums
+    #pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int ib = g0 + 8 * (8 * h + s);
+                        if (!kFull && ib >= D) continue;      // warp-uniform: dead slot of the partial half
+                        const int i = ib + j;
+                        if (kFull || i < D) {
+                            R t0 = th[s];
+                            if (pend) {
+                                t0 = t0 + cp * (R)xo[s];
+                                row[i] = t0;
                             }
-                            continue;
+                            if (emit) drow[i] = t0;           // the state after the previous draw (moved or not)
+                            R x;
+                            if constexpr (kReplay) {
+                                x = reinterpret_cast<const R*>(a.rho)[c * D + i];
+                                xr[i] = (XT)x;
+                            } else {
+                                const float xf = fmaf(s_sd[i], z[s], has_mean ? mcol_s[i] : 0.0f);
+                                xr[i] = (XT)xf;
+                                x = (R)xf;
+                            }
+                            const R xt = x + tol;
+                            ss += xt * xt;
+                            const R xw = x * (KLHR_TILE_W_SMEM ? s_w[i] : Model::wgt(i, a.mp));
+                            sA += x * xw;
+                            sB += t0 * xw;
                         }
                     }
-                    if (pend_rt) {
-                        if (full) do_half(std::true_type{}, std::true_type{}, std::false_type{}, g0, h);
-                        else do_half(std::false_type{}, std::true_type{}, std::false_type{}, g0, h);
-                    } else {
-                        if (full) do_half(std::true_type{}, std::false_type{}, std::false_type{}, g0, h);
-                        else do_half(std::false_type{}, std::false_type{}, std::false_type{}, g0, h);
+                };
+                for (int g0 = 0; g0 < D; g0 += 128) {
+    #pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        if (g0 + 64 * h >= D) break;          // warp-uniform: nothing left
+                        const bool full = g0 + 64 * h + 63 < D;
+                        if constexpr (kDraws) {
+                            if (emit_rt) {                    // warp-uniform (thinned sample() output)
+                                if (pend_rt) {
+                                    if (full) do_half(std::true_type{}, std::true_type{}, std::true_type{}, g0, h);
+                                    else do_half(std::false_type{}, std::true_type{}, std::true_type{}, g0, h);
+                                } else {
+                                    if (full) do_half(std::true_type{}, std::false_type{}, std::true_type{}, g0, h);
+                                    else do_half(std::false_type{}, std::false_type{}, std::true_type{}, g0, h);
+                                }
+                                continue;
+                            }
+                        }
+                        if (pend_rt) {
+                            if (full) do_half(std::true_type{}, std::true_type{}, std::false_type{}, g0, h);
+                            else do_half(std::false_type{}, std::true_type{}, std::false_type{}, g0, h);
+                        } else {
+                            if (full) do_half(std::true_type{}, std::false_type{}, std::false_type{}, g0, h);
+                            else do_half(std::false_type{}, std::false_type{}, std::false_type{}, g0, h);
+                        }
                     }
                 }
             }
-            ss = oct_sum(ss, om);
-            sA = oct_sum(sA, om);
-            sB = oct_sum(sB, om);
-            if (j == p) { my_ss = ss; my_A = sA; my_B = sB; }
+            ss = warp_oct_sum(ss);
+            sA = warp_oct_sum(sA);
+            sB = warp_oct_sum(sB);
+            if (j == p && c < a.B) { my_ss = ss; my_A = sA; my_B = sB; }
         }
         // -------------------------------------------------------------------- fit phase (thread per chain)
         R inv = 1;
