@@ -153,3 +153,44 @@ def test_draws_parquet_round_trip(tmp_path):
     assert write_draws(tmp_path / "one.parquet", one, ["x", "y", "z"]) == 4
     with __import__("pytest").raises(ValueError):
         write_draws(tmp_path / "bad.parquet", draws, ["a"])
+
+
+def test_argument_validation_of_every_entry_point_without_a_gpu():
+    """Every export validates its arguments before any CUDA call: NULL descriptors, bad dtypes, negative sizes
+    and inconsistent slice / direction settings come back as negative codes with a message; empty batches are 0."""
+    import ctypes as C
+    from klhr_b200 import _lib
+    lib = _lib.load()
+    model = _lib.ModelDesc(id=0, dim=4)
+    fit = _lib.FitDesc(family=0, n_nodes=8, n1=12, n2=24, nb=8, initscale=0.1, tol=1e-12, scale_clip=600.0,
+                       gtol1=1e-4, gtol2=1e-10, step_cap=2.0, c1=1e-4, basin=1e-3)
+    sl = _lib.SliceDesc(w=1.0, lower=-float("inf"), upper=float("inf"), tol=1e-12, cap=8)
+    acc = _lib.AccumDesc(thin=1)
+    m, f, s = C.byref(model), C.byref(fit), C.byref(sl)
+    # empty batches succeed without touching the device
+    assert lib.klhr_run(m, f, None, 0, None, 0, 0, 0, 5, 1, None, None, None) == 0
+    assert lib.klhr_slice_run(m, s, None, 0, None, 0, 0, 0, 5, 1, None, None, None) == 0
+    assert lib.klhr_slice_replay(m, s, 0, None, None, None, None, None, None, 0, None) == 0
+    assert lib.klhr_kl_eval(m, f, 0, None, None, None, None, None, None, 0, None) == 0
+    assert lib.klhr_mh_run(m, 0, None, 0.5, 0, 0, 0, 3, 1, None, None, None) == 0
+    assert lib.klhr_math_eval(0, None, None, 0, None) == 0
+    # NULL buffers with a non-empty batch
+    assert lib.klhr_run(m, f, None, 0, None, 8, 0, 0, 5, 1, None, None, None) < 0 and "theta" in _lib.last_error()
+    assert lib.klhr_kl_eval(m, f, 0, None, None, None, None, None, None, 8, None) < 0
+    assert lib.klhr_slice_replay(m, s, 0, None, None, None, None, None, None, 8, None) < 0
+    assert lib.klhr_math_eval(2, None, None, 4, None) < 0 and "op" in _lib.last_error()
+    # bad descriptors
+    assert lib.klhr_run(None, f, None, 0, None, 8, 0, 0, 5, 1, None, None, None) < 0
+    assert lib.klhr_run(m, None, None, 0, None, 8, 0, 0, 5, 1, None, None, None) < 0
+    assert lib.klhr_run(m, f, None, 7, None, 8, 0, 0, 5, 1, None, None, None) < 0 and "dtype" in _lib.last_error()
+    assert lib.klhr_run(m, f, None, 0, None, -1, 0, 0, 5, 1, None, None, None) < 0
+    bad = _lib.SliceDesc(w=0.0, lower=-1.0, upper=1.0, tol=0.0, cap=8)
+    assert lib.klhr_slice_run(m, C.byref(bad), None, 0, None, 8, 0, 0, 5, 1, None, None, None) < 0 and "w" in _lib.last_error()
+    bad = _lib.SliceDesc(w=1.0, lower=0.5, upper=1.0, tol=0.0, cap=8)
+    assert lib.klhr_slice_run(m, C.byref(bad), None, 0, None, 8, 0, 0, 5, 1, None, None, None) < 0
+    bad_model = _lib.ModelDesc(id=99, dim=4)
+    assert lib.klhr_model_eval(C.byref(bad_model), 0, None, None, None, 0, None) < 0
+    pooled_only_s1 = _lib.AccumDesc(thin=1, pooled_s1=1)
+    assert lib.klhr_run(m, f, None, 0, None, 8, 0, 0, 5, 1, C.byref(pooled_only_s1), None, None) < 0
+    assert lib.klhr_outer_scratch_doubles(0, 10) == 0 and lib.klhr_outer_scratch_doubles(1000, 10) > 0
+    del acc
