@@ -562,3 +562,47 @@ def test_adaptation_variants_scale_dir_cov_and_method_two():
         z = np.abs(summ["mean"].cpu().numpy()) / summ["mcse_mean"].cpu().numpy()
         zv = np.abs(summ["var"].cpu().numpy() - truth) / summ["mcse_var"].cpu().numpy()
         assert z.max() <= 4.5 and zv.max() <= 4.5, (cls.__name__, kw, z.max(), zv.max())
+
+
+def test_raw_ctypes_binding_of_integration_md():
+    """The stand-alone ctypes stubs INTEGRATION.md shows a maintainer (no klhr_b200 imports): batched model
+    evaluation and a klhr_run launch on the raw library."""
+    import ctypes as C
+    from pathlib import Path
+    lib = C.CDLL(str(Path(kb.__file__).resolve().parent / "libklhr_sm100.so"))
+
+    class klhr_model_t(C.Structure):
+        _fields_ = [("id", C.c_int32), ("dim", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32),
+                    ("s0", C.c_double), ("s1", C.c_double), ("data0", C.c_void_p), ("data1", C.c_void_p)]
+
+    class klhr_fit_t(C.Structure):
+        _fields_ = [("family", C.c_int32), ("n_nodes", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
+                    ("nb", C.c_int32), ("flags", C.c_int32), ("kmax", C.c_int32), ("overrelax_K", C.c_int32),
+                    ("initscale", C.c_double), ("tol", C.c_double), ("scale_clip", C.c_double),
+                    ("gtol1", C.c_double), ("gtol2", C.c_double), ("step_cap", C.c_double), ("c1", C.c_double),
+                    ("basin", C.c_double), ("x", C.c_double * 32), ("w", C.c_double * 32)]
+
+    D, B, seed = 20, 4096, 5
+    s = torch.arange(1, D + 1, dtype=torch.float64, device=device()) / D ** 0.5
+    inv_s2 = (1 / (s * s)).contiguous()
+    m = klhr_model_t(id=1, dim=D, data0=inv_s2.data_ptr())
+    lib.klhr_model_eval.restype = C.c_int
+    lib.klhr_model_eval.argtypes = [C.POINTER(klhr_model_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    theta = 0.1 * torch.randn(B, D, dtype=torch.float64, device=device())
+    lp = torch.empty(B, dtype=torch.float64, device=device())
+    grad = torch.empty_like(theta)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.klhr_model_eval(C.byref(m), 0, theta.data_ptr(), lp.data_ptr(), grad.data_ptr(), B, st) == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(lp, -0.5 * (theta ** 2 * inv_s2).sum(1)) and torch.allclose(grad, -theta * inv_s2)
+    x, w = np.polynomial.hermite.hermgauss(8)
+    fit = klhr_fit_t(family=0, n_nodes=8, n1=12, n2=24, nb=8, initscale=0.1, tol=1e-12, scale_clip=600.0,
+                     gtol1=1e-4, gtol2=1e-10, step_cap=2.0, c1=1e-4, basin=1e-3)
+    fit.x[:8], fit.w[:8] = list(x * np.sqrt(2)), list(w / np.sqrt(np.pi))
+    lib.klhr_run.restype = C.c_int
+    rc = lib.klhr_run(C.byref(m), C.byref(fit), None, 0, C.c_void_p(theta.data_ptr()), C.c_int64(B), C.c_int64(0),
+                      C.c_int64(0), C.c_int32(1500), C.c_uint64(seed), None, None, C.c_void_p(st))
+    assert rc == 0
+    torch.cuda.synchronize()
+    v = theta.var(0).cpu().numpy()                      # isotropic hit-and-run on ill-normal: var_i -> i^2 / D
+    assert np.allclose(v, np.arange(1, D + 1) ** 2 / D, rtol=0.2)
