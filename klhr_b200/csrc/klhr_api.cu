@@ -83,8 +83,8 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     return 0;
 }
 
-// The tile kernel covers: diagonal-Gaussian targets, Gaussian family, no in-kernel accumulators
-// and no thinned-draw output.  Everything else runs on the general octet kernel.
+// The tile kernel covers: diagonal-Gaussian targets, Gaussian family, no in-kernel moment accumulators
+// (thinned draws are written by a second instantiation).  Everything else runs on the chain or octet kernel.
 static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
     // at most 2 stored direction-mean columns: they live in the tile's shared memory (J = 2 default)
     const int n_stored = a.dir.mean_cols ? a.dir.n_cols - a.dir.n_zero_cols : 0;
