@@ -158,8 +158,14 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+            import atexit
+            atexit.register(self._kill)                  # never leave the sampler behind if the bench dies
         except OSError:
             pass
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
 
     def stop(self, t_begin=None, t_end=None):
         """Median SM clock and active throttle reasons over samples inside [t_begin, t_end]
