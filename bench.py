@@ -4,19 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): stan/ill-normal, D = 100 diagonal Gaussian, 65 536 chains
-per GPU, Gaussian line family, fp64, reference warm-up schedule [50, 150, 350, 1000] run
-before the timed region.  One "step" = every chain advanced by --draws-per-step KLHR draws
-(one `klhr_run` launch).  N > 1 shards chains over ranks (weak scaling, no collective in the
-step; the only NCCL traffic is the pooled-adaptation allreduce at window closures, which
-happen in the untimed adaptation phase).
+Headline workload (BASELINE.json configs[1]): stan/ill-normal, D = 100 diagonal Gaussian, 65 536 chains per GPU,
+Gaussian line family, fp64, reference warm-up schedule [50, 150, 350, 1000] run (and timed separately) before the
+timed region.  One "step" = every chain advanced by --draws-per-step KLHR draws (one `klhr_run` launch).  N > 1
+shards chains over ranks (weak scaling, no collective in the step).
 
-The timed number `value` has chain state resident in HBM; `e2e` re-uploads the start state
-from pinned host memory and reads the final state back every step through the public sampler
-API.  `--impl reference` times the reference's own CPU implementation of the same step (the
-SciPy-BFGS single-chain port in oracle/ref_port.py, one process per chain on all host cores,
-like reference run_experiments:27) -- /root/reference itself is pure Python and is not
-present on the GPU box, so `cpu_baseline.kind` is "port".
+The JSON line also carries
+  peaks     FP64 / FP32 FMA, FP64 DMMA and Philox+Box-Muller normals per second measured in this process with the
+            micro-kernels of csrc/klhr_probe.cu (BASELINE.md section 3: the vector peaks are not in MEASURED_PEAKS.json);
+  roofline  the slower of (FP64 flops executed / measured FP64 peak) and (HBM bytes / measured HBM peak), plus the
+            direction-normal rate against its measured ceiling (the resource the kernel actually runs against);
+  adapt     the warm-up phase: wall time of the 1000 adaptation draws including the pooled all-reduce at each of the
+            4 window closures (the only collective of the path) -- max over ranks;
+  e2e       the metric through the public sampler API from pinned HOST buffers; e2e_sample: MCMCBase.sample's own
+            contract (every draw returned, mcmc.py:31-37) streamed to pinned host memory;
+  configs   BASELINE.json configs[2..4] (funnel + sinh-arcsinh family, dense corr-normal D = 256, arK T = 10 000)
+            measured the same way, each with its roofline and its adaptation phase (c5 is the config whose
+            closure all-reduce runs over every rank of --gpus N).
+
+`--impl reference` times the reference's own CPU implementation of the same step (the SciPy-BFGS single-chain port in
+oracle/ref_port.py, one process per chain on all host cores, like reference run_experiments:27) -- /root/reference
+itself is pure Python and is not present on the GPU box, so `cpu_baseline.kind` is "port".
 """
 from __future__ import annotations
 
@@ -48,9 +56,10 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=100)
     ap.add_argument("--draws-per-step", type=int, default=1000)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--adapt-warmup", type=int, default=1000, help="sampler warm-up draws (untimed)")
+    ap.add_argument("--adapt-warmup", type=int, default=1000, help="sampler warm-up draws (timed separately)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip configs c3..c5)")
     ap.add_argument("--ref-draws-per-step", type=int, default=400)
     ap.add_argument("--ref-procs", type=int, default=0, help="0 = all host cores")
     return ap.parse_args()
@@ -150,10 +159,12 @@ class ClockSampler:
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.rows = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
@@ -167,55 +178,66 @@ class ClockSampler:
         if self.proc is not None and self.proc.poll() is None:
             self.proc.kill()
 
-    def stop(self, t_begin=None, t_end=None):
-        """Median SM clock and active throttle reasons over samples inside [t_begin, t_end]
-        (time.time() stamps of the timed region); all samples if the window holds none."""
+    def stop(self):
         import datetime
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
-            return out
+            self.rows = []
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.tmp.flush()
-        rows = [r.split(",") for r in Path(self.tmp.name).read_text().splitlines() if r.count(",") >= 7]
-        os.unlink(self.tmp.name)
-        sm, reasons = [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        mx = None
-        def stamp(s):
+        rows = []
+        for r in Path(self.tmp.name).read_text().splitlines():
+            f = r.split(",")
+            if len(f) < 8:
+                continue
             try:
-                return datetime.datetime.strptime(s.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
-            except ValueError:
-                return None
-        if t_begin is not None:
-            inside = [r for r in rows if (stamp(r[0]) or 0) >= t_begin - 0.05 and (stamp(r[0]) or 0) <= t_end + 0.05]
-            out["samples_total"] = len(rows)
-            rows = inside or rows
-        for r in rows:
-            try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
+                ts = datetime.datetime.strptime(f[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [x.strip().lower().startswith("active") for x in f[4:8]]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if r[4 + k].strip().lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self.tmp.name)
+        self.rows = rows
+
+    def window(self, t_begin, t_end):
+        """Median SM clock and active throttle reasons over the samples stamped inside [t_begin, t_end]
+        (time.time() stamps); all samples if the window holds none (a region shorter than the 50 ms period)."""
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        rows = self.rows or []
+        inside = [r for r in rows if t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        use = inside or rows
+        if not use:
+            return out
+        sm = sorted(r[1] for r in use)
+        reasons = sorted({self.NAMES[k] for r in use for k in range(4) if r[3][k]})
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=use[-1][2], reasons=reasons, samples=len(inside),
+                   samples_total=len(rows))
         return out
 
 
 # =============================================================================== B200 arm
+def ark_series(T=10_000, K=5):
+    """y_t = 0.2 + sum_k beta_k y_{t-6+k} + 0.5 eps_t, seeded, 500 burn-in dropped."""
+    import numpy as np
+    beta = np.array([0.05, -0.10, 0.15, -0.20, 0.60])
+    rng = np.random.default_rng(20261018)
+    eps = rng.normal(size=T + 500)
+    y = np.zeros(T + 500)
+    for t in range(K, T + 500):
+        y[t] = 0.2 + beta @ y[t - K:t] + 0.5 * eps[t]
+    return y[500:]
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import klhr_b200 as kb
+    from klhr_b200 import engine
     from klhr_b200.diagnostics import chain_summary
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,7 +248,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     # started first: nvidia-smi can take a second to spin up on a fresh box, and only samples stamped inside the
-    # timed region are used
+    # timed regions are used
     clocks = ClockSampler(local) if rank == 0 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -234,43 +256,101 @@ def run_b200(args):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     B, D, S, K, W = args.chains, args.dim, args.draws_per_step, args.steps, args.warmup
     rb = 8 if dtype == torch.float64 else 4
-
-    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": D}, device=dev)
-    sampler = kb.KLHR(model, seed=SEED, chains=B, warmup=args.adapt_warmup, windowsize=50, windowscale=2,
-                      dtype=dtype, device=dev)
-    sampler.run(args.adapt_warmup)            # adaptation phase: windows close at 50,150,350,1000 (+ allreduce)
-    torch.cuda.synchronize()
+    launches = [0]                                   # klhr_run launches inside timed regions (gpu_launches)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    # ---------------------------------------------------------------- resident arm
-    for _ in range(W):
-        sampler.run(S)
-    torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    wall0 = time.time()
-    for k in range(K):
-        flush.zero_()                          # L2 flush between timed iterations (state is 52 MB < L2)
-        evs[k][0].record()
-        sampler.run(S)                         # ONE klhr_run launch: B chains x S draws
-        evs[k][1].record()
-    torch.cuda.synchronize()
-    barrier()
-    wall = time.perf_counter() - t0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    dev_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(dev_ms.item())
-    clk = clocks.stop(wall0, time.time()) if clocks else None
+    # ---------------------------------------------------------------- peaks (micro-kernels, this process, this GPU)
+    peaks = {
+        "fp64_fma_tflops": 2e-12 * engine.peak_probe("fp64_fma", dev),
+        "fp32_fma_tflops": 2e-12 * engine.peak_probe("fp32_fma", dev),
+        "fp64_dmma_tflops": 16e-12 * engine.peak_probe("fp64_dmma", dev),
+        "normals_per_s": engine.peak_probe("normals", dev),
+        "how": "csrc/klhr_probe.cu, 8 CTAs x 256 threads per SM, best of 5 launches, CUDA events; normals = "
+               "Philox4x32-10 + fp32 Box-Muller exactly as in the step kernels",
+    }
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        hbm_peak, hbm_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peaks["hbm_gbs"] = hbm_peak
+    prof = {}
+    pp = ROOT / "profiles" / "ncu_counts.json"          # per-chain-draw instruction / flop / DRAM counts from ncu captures
+    if pp.exists():
+        prof = json.loads(pp.read_text())
+
+    def adapt_phase(sampler, n):
+        """The warm-up: n adaptation draws incl. the pooled all-reduce + host eigendecomposition at each closure."""
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sampler.run(n)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    def timed_steps(sampler, draws, k, w, do_flush):
+        """k launches of `draws` draws, each bracketed by CUDA events on the launching stream; max over ranks of
+        the summed device time.  Returns (total_ms, wall window)."""
+        for _ in range(w):
+            sampler.run(draws)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        torch.cuda.synchronize()
+        w0 = time.time()
+        for i in range(k):
+            if do_flush:
+                flush.zero_()                      # L2 flush between timed iterations
+            evs[i][0].record()
+            sampler.run(draws)                     # ONE klhr_run launch: all chains x `draws` draws
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        barrier()
+        w1 = time.time()
+        launches[0] += k
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), (w0, w1)
+
+    def fp64_roofline(name, value_per_gpu, hbm_bytes_per_draw, peak_tflops, peak_name, kernel, note):
+        """Slower of FP64 and HBM (north star); flops per chain-draw are COUNTED by ncu on the same kernel and
+        configuration (profiles/ncu_counts.json: (dadd + dmul + 2 dfma [+ 512 dmma]) / chain-draws)."""
+        c = prof.get(name, {})
+        flops = c.get("fp64_flops_per_draw")
+        out = {"kernel": kernel, "hbm_bytes_per_chain_draw": hbm_bytes_per_draw,
+               "hbm_gbs_achieved": hbm_bytes_per_draw * value_per_gpu / 1e9, "hbm_frac": hbm_bytes_per_draw * value_per_gpu / 1e9 / hbm_peak,
+               "fp64_flops_per_chain_draw": flops, "warp_instructions_per_chain_draw": c.get("warp_inst_per_draw"),
+               "issue_active_pct": c.get("issue_active_pct"), "traffic": c.get("dram_bytes_per_launch"),
+               "traffic_launch": c.get("launch"), "counts_source": "profiles/ncu_counts.json (ncu --set full, same kernel and shape)" if c else None,
+               "note": note}
+        if flops:
+            ach = flops * value_per_gpu / 1e12
+            t_f, t_b = flops / (peak_tflops * 1e12), hbm_bytes_per_draw / (hbm_peak * 1e9)
+            out.update(bound="fp64" if t_f >= t_b else "hbm", achieved=ach if t_f >= t_b else out["hbm_gbs_achieved"],
+                       peak=peak_tflops if t_f >= t_b else hbm_peak, unit="TFLOP/s" if t_f >= t_b else "GB/s",
+                       frac=(ach / peak_tflops) if t_f >= t_b else out["hbm_frac"], peak_source=f"measured in this run ({peak_name})" if t_f >= t_b else hbm_src)
+        else:
+            out.update(bound="hbm", achieved=out["hbm_gbs_achieved"], peak=hbm_peak, unit="GB/s", frac=out["hbm_frac"],
+                       peak_source=hbm_src)
+        return out
+
+    # =============================================================== headline: ill-normal D = 100 (configs[1])
+    model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": D}, device=dev)
+    sampler = kb.KLHR(model, seed=SEED, chains=B, warmup=args.adapt_warmup, windowsize=50, windowscale=2,
+                      dtype=dtype, device=dev)
+    adapt_s = adapt_phase(sampler, args.adapt_warmup)     # windows close at 50,150,350,1000 (+ all-reduce)
+    total_ms, (wall0, wall1) = timed_steps(sampler, S, K, W, True)
     value = world * B * S * K / (total_ms * 1e-3)
+    info = kb.launch_info(model, sampler._fit, dtype=dtype, free_running=True, accumulate=False, device=dev)
 
     # ---------------------------------------------------------------- end-to-end arm (host buffers)
     # Every step: H2D of the step's start state from pinned host memory, S draws through the public
@@ -316,11 +396,30 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     barrier()
+    launches[0] += K
     sampler.swap_state(bufs[0])
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * S * K / (float(e2e_ms.item()) * 1e-3)
+    e2e_value = world * B * S * K / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+
+    # ---------------------------------------------------------------- e2e of MCMCBase.sample's own contract
+    # sample(M) returns EVERY draw (mcmc.py:31-37): 800 B per chain-draw must cross PCIe, which bounds the
+    # host-visible rate; the rows are streamed to pinned host memory in chunks, D2H of chunk k-1 under the kernel
+    # of chunk k (KLHR.sample(out=...)).
+    M_rows = 17
+    rows_host = torch.empty(M_rows, B, D, dtype=dtype).pin_memory()
+    sampler.sample(M_rows, thin=1, out=rows_host, chunk_rows=4)          # warm-up (allocations, first touch)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sampler.sample(M_rows, thin=1, out=rows_host, chunk_rows=4)
+    torch.cuda.synchronize()
+    samp_s = max_over_ranks(time.perf_counter() - t0)
+    launches[0] += 4
+    e2e_sample = {"value": world * B * (M_rows - 1) / samp_s, "unit": UNIT, "rows": M_rows, "thin": 1,
+                  "d2h_bytes_per_call": M_rows * B * D * rb, "d2h_gbs_per_gpu": M_rows * B * D * rb / samp_s / 1e9,
+                  "bound": f"PCIe D2H: {D * rb} B per chain-draw",
+                  "api": "KLHR.sample(M, thin=1, out=pinned host tensor): every draw returned (mcmc.py:31-37), chunks of 4 rows "
+                         "double-buffered on the device, D2H on a copy stream under the next chunk's kernel; host wall clock"}
+    del rows_host
 
     # ---------------------------------------------------------------- ESS per draw (diagnostic pass)
     ess = None
@@ -337,7 +436,7 @@ def run_b200(args):
         zvar = ((summ["var"] - truth).abs() / summ["mcse_var"]).max()
         ess_min = float(summ["ess"].min())
         ms = a0.elapsed_time(a1)
-        # ESS per draw is a property of the chains (both kernels draw the same streams); the pass that
+        # ESS per draw is a property of the chains (all kernels draw the same streams); the pass that
         # measures it needs per-chain sums and therefore runs on the accumulating octet kernel, so
         # ESS/sec of the production path = ESS per chain-draw x the timed chain-draws/sec
         ess = {"min_ess_per_sec": (ess_min / (B * S_ess)) * value, "min_ess_per_draw": ess_min / (B * S_ess),
@@ -345,21 +444,92 @@ def run_b200(args):
                "draws_per_chain": S_ess, "estimator": "between-chain variance of chain means, B independent chains",
                "max_abs_z_mean": float(zmean), "max_abs_z_var": float(zvar),
                "acceptance": sampler.acceptance_probability}
+        del s1, s2
 
+    kernel_name = ("klhr::lane_kernel (csrc/klhr_lane.cuh)" if info["threads"] in (32, 64) and info["smem"] > 30000 else
+                   "klhr::tile_kernel (csrc/klhr_tile.cuh)" if info["threads"] == 32 else "klhr::step_kernel (csrc/klhr_step.cuh)")
+    n_gen = 16 * (2 * (D // 32) + (2 if D % 32 > 4 else (1 if D % 32 else 0)))       # normals generated per chain-draw (16 per trip)
+    roof = fp64_roofline(
+        "c2", value / world, (2 * D * rb + 16) / S, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", kernel_name,
+        f"S = {S} draws are fused per launch with theta resident in shared memory: HBM sees one read and one write of "
+        f"theta per LAUNCH, i.e. (2 D {rb} + 16) / S bytes per chain-draw (SURVEY 8d); the FP64 side counts the flops the "
+        "kernel executes (closed-form quadratic fit, not the reference-equivalent 14 evaluations); neither is what "
+        "bounds the kernel -- see `normals`")
+    roof["normals"] = {"generated_per_chain_draw": n_gen, "used_per_chain_draw": D,
+                       "achieved_per_s": n_gen * value / world, "peak_per_s": peaks["normals_per_s"],
+                       "frac": n_gen * value / world / peaks["normals_per_s"],
+                       "note": "the D direction normals per chain-draw (klhr.py:143-153) are the dominant instruction stream; "
+                               "peak = the same Philox4x32-10 + Box-Muller code alone at full occupancy"}
+    roof["draws_fused_per_launch"] = S
+
+    line = None
+    cfg_lines = {}
+    # =============================================================== configs[2..4]
+    if not args.no_configs:
+        Kc = max(3, min(K, 5))
+
+        def run_config(tag, workload, make_sampler, draws, hbm_bytes_per_draw, peak_tflops, peak_name, kernel, note, extra=None):
+            smp = make_sampler()
+            a_s = adapt_phase(smp, 1000)
+            a_draws = world * smp.chains * 1000
+            t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, 2, False)
+            val = world * smp.chains * draws * Kc / (t_ms * 1e-3)
+            ev0 = int(smp._evals_total.item())
+            smp.run(draws)
+            evals = (int(smp._evals_total.item()) - ev0) / (smp.chains * draws)
+            out = {"workload": workload, "value": val, "unit": UNIT, "ms_per_step": t_ms / Kc, "steps": Kc,
+                   "draws_per_step": draws, "chains_per_gpu": smp.chains, "acceptance": smp.acceptance_probability,
+                   "line_evaluations_per_draw": evals,
+                   "adapt": {"draws": 1000, "closures": smp._windowedadaptation.closures, "phase_s": a_s,
+                             "chain_draws_per_s": a_draws / a_s, "frac_of_steady_state": a_draws / a_s / val},
+                   "roofline": fp64_roofline(tag, val / world, hbm_bytes_per_draw / draws, peak_tflops, peak_name, kernel, note),
+                   "window": (c0_, c1_), "inputs": "state (chains x D fp64) larger than L2" if smp.chains * smp.D * 8 > 126e6
+                   else "state smaller than L2; kernels keep it on-chip for the whole launch, so no flush is needed between steps"}
+            if extra:
+                out.update(extra(smp))
+            del smp
+            torch.cuda.empty_cache()
+            return out
+
+        fm = kb.BSModel(stan_file="stan/funnel.stan", data={"D": 1}, device=dev)
+        cfg_lines["c3"] = run_config(
+            "c3", "stan/funnel dims=2 (stan/funnel.json), KLHRSINH sinh-arcsinh line fit, overrelaxed=False, 262144 chains/GPU, fp64",
+            lambda: kb.KLHRSINH(fm, seed=SEED, chains=262_144, warmup=1000, overrelaxed=False, device=dev), 20,
+            2 * 2 * 8 + 16, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", "klhr::chain_kernel (csrc/klhr_chain.cuh)",
+            "thread-per-chain 4-parameter Newton fit on the O(1) line restriction; bound by fp64 arithmetic incl. exp/log",
+        )
+        cm = kb.BSModel(stan_file="stan/corr-normal.stan", data={"N": 256, "rho": 0.9}, device=dev)
+        cfg_lines["c4"] = run_config(
+            "c4", "stan/corr-normal D=256 dense precision (Sigma_ij = 0.9^|i-j|), KLHR Gaussian line fit, 16384 chains/GPU, fp64",
+            lambda: kb.KLHR(cm, seed=SEED, chains=16_384, warmup=1000, device=dev), 100,
+            2 * 256 * 8 + 16, peaks["fp64_dmma_tflops"], "peaks.fp64_dmma_tflops", "klhr::step_kernel + klhr_dense.cuh (DMMA)",
+            "P rho for all chains of a CTA on mma.sync.m8n8k4.f64: 2 D^2 = 131 kflop per chain-draw (SURVEY 8d)")
+        ak = kb.BSModel(stan_file="stan/arK.stan", data={"K": 5, "T": 10_000, "y": ark_series().tolist()}, device=dev)
+
+        def ark_extra(smp):
+            s1_, s2_ = smp.run(200, chain_stats=True)
+            mean = chain_summary(s1_, s2_, 200)["mean"].cpu().numpy()
+            if world > 1:
+                mt = torch.as_tensor(mean, device=dev)
+                dist.all_reduce(mt)
+                mean = (mt / world).cpu().numpy()
+            return {"posterior_mean": [round(float(x), 4) for x in mean],
+                    "generating_values": [0.2, 0.05, -0.10, 0.15, -0.20, 0.60, round(float(np.log(0.5)), 4)]}
+        cfg_lines["c5"] = run_config(
+            "c5", f"stan/arK K=5 T=10000 synthetic (BASELINE.md 4.5), KLHR Gaussian line fit, 131072 chains/GPU "
+                  f"({world * 131_072} chains over {world} GPU(s)), pooled windowed-adaptation all-reduce at 4 closures",
+            lambda: kb.KLHR(ak, seed=SEED, chains=131_072, warmup=1000, device=dev), 100,
+            2 * 7 * 8 + 16, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", "klhr::chain_kernel (csrc/klhr_chain.cuh)",
+            "line restriction through the Gram matrix X'X (6x6), X'y, y'y: ~100 flop per evaluation instead of 2.6e5 for the "
+            "direct T-loop (SURVEY 8a M6); the adaptation phase contains the only collective of the path", ark_extra)
+
+    if clocks:
+        clocks.stop()
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        bytes_per_draw = 2 * D * rb + 16                        # theta read + write + scalars
-        launch_ms = total_ms / K                                 # one step-kernel launch per step
-        achieved = bytes_per_draw * B * S / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "ncu_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-        info = kb.launch_info(model, sampler._fit, dtype=dtype, free_running=True, accumulate=False, device=dev)
+        clk = clocks.window(wall0, wall1)
+        for c in cfg_lines.values():
+            c["clocks"] = clocks.window(*c.pop("window"))
+        adapt_draws = world * B * args.adapt_warmup
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -368,25 +538,25 @@ def run_b200(args):
                                    f"line fit, {S} draws per step (one launch)",
                        "chains_per_gpu": B, "global_chains": world * B, "dim": D, "draws_per_step": S,
                        "adapt_warmup_draws": args.adapt_warmup, "windows": sampler._windowedadaptation.closures,
-                       "parallelism": f"chains sharded over {world} GPU(s), no collective in the step",
+                       "parallelism": f"chains sharded over {world} GPU(s), no collective in the step; one all-reduce of "
+                                      "pooled moment / PCA sums per window closure (inside `adapt`)",
                        "l2": "256 MB memset between timed steps (state 52 MB < 126 MB L2); excluded from "
-                             "ms_per_step by per-step CUDA events", "seed": SEED,
-                       "launch": info, "wall_s_incl_flush": wall},
+                             "ms_per_step by per-step CUDA events", "seed": SEED, "launch": info},
             "clocks": clk,
+            "peaks": peaks,
+            "adapt": {"draws": args.adapt_warmup, "closures": sampler._windowedadaptation.closures, "phase_s": adapt_s,
+                      "chain_draws_per_s": adapt_draws / adapt_s, "frac_of_steady_state": adapt_draws / adapt_s / value,
+                      "contains": "adaptation launches, pooled moment/PCA accumulation, 4 x all-reduce(SUM, fp64) of "
+                                  f"(2 + 4 D + D^2) doubles = {(2 + 4 * D + D * D) * 8} B over {world} rank(s), host eigh; wall clock, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * rb,
                     "d2h_bytes_per_step": B * D * rb + B * 8,
                     "api": "KLHR.run(draws_per_step) from a pinned host start state, final state + accept counts "
                            "read back every step; copies of neighbouring steps overlap the kernel (2 buffers, 3 streams)"},
-            "gpu_launches": K,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": ("klhr::tile_kernel (csrc/klhr_tile.cuh)" if info["threads"] == 32 else
-                                    "klhr::step_kernel (csrc/klhr_step.cuh)"),
-                         "algorithmic_bytes_per_chain_draw": bytes_per_draw,
-                         "note": f"achieved = SURVEY 8(d) algorithmic bytes x chain-draws / launch time; {S} draws are "
-                                 "fused per launch and theta (52 MB) stays L2-resident between draws, so DRAM "
-                                 "traffic (ncu) is far below the algorithmic bytes"},
+            "e2e_sample": e2e_sample,
+            "gpu_launches": launches[0],
+            "roofline": roof,
             "ess": ess,
+            "configs": cfg_lines,
         }
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_baseline(D, 2000, args.ref_procs, args.adapt_warmup)

@@ -59,6 +59,9 @@ typedef struct klhr_model {
  * kernels (tile kernel: diagonal-Gaussian targets with the Gaussian family; chain kernel: every
  * other case whose rho tile fits in shared memory) apply -- the parity tests cover both paths */
 #define KLHR_FIT_FORCE_OCTET 1
+/* run the tile kernel (theta streamed through L2, octet-cooperative sweep) where the lane kernel (thread per
+ * chain, theta resident in shared memory) would be chosen -- the parity tests cover both */
+#define KLHR_FIT_FORCE_TILE 4
 /* sinh family with the tail-weight parameter frozen at d = 1: the 3-parameter variant of reference
  * sub_klhr_sinh.py (SUBKLHRSINH); eta is still reported as (m, log s, 0, e) */
 #define KLHR_FIT_FIX_D 2
@@ -233,6 +236,18 @@ int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim);
  * kernel would be launched with for this problem; returns resident CTAs per SM (<=0 error). */
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running,
                      int accumulate, int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* regs);
+
+/* Test hook: out[i][0..3] = Philox4x32-10(counter = in[i][0..3], key = in[i][4..5]) with the generator the step
+ * kernels use (csrc/klhr_common.cuh), for the Random123 known-answer vectors (tests/test_gpu_philox.py). */
+int klhr_philox_eval(const uint32_t* ctr_key_dev, uint32_t* out_dev, int64_t n, void* stream);
+
+/* Peak probes for the roofline denominators (the FP64 / FP32 vector peaks are not in
+ * MEASURED_PEAKS.json and must be measured with an FMA micro-kernel on the box).  Launches `ctas` CTAs of 256
+ * threads running `iters` trips of micro-kernel `kind` (0 fp64 FMA, 1 Philox4x32-10 + fp32 Box-Muller normals --
+ * the direction stream of the step --, 2 fp32 FMA, 3 cvt.f64.f32, 4 MUFU, 5 mul.wide.u32, 6 integer-pipe
+ * fp32->fp64 promotion, 7 fp64 DMMA m8n8k4) asynchronously on `stream`; the caller times it.  Returns the number of operations the
+ * launch issues (thread-level: one FMA = one operation = 2 flop), or < 0 on a bad argument. */
+int64_t klhr_peak_probe(int kind, int64_t iters, int ctas, double* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

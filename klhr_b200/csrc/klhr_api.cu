@@ -7,6 +7,7 @@
 #include <string>
 
 #include "klhr_chain.cuh"
+#include "klhr_lane.cuh"
 #include "klhr_mh.cuh"
 #include "klhr_slice.cuh"
 
@@ -85,6 +86,16 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
 
 // The tile kernel covers: diagonal-Gaussian targets, Gaussian family, no in-kernel moment accumulators
 // (thinned draws are written by a second instantiation).  Everything else runs on the chain or octet kernel.
+// The lane kernel (thread per chain, theta resident in shared memory, closed-form quadratic fit) takes the
+// free-running fp64 launches of the same cases whenever at least 4 one-warp CTAs fit per SM (D <= ~115 with two
+// stored mean columns); replay, fp32, over-relaxed proposals and larger D stay on the tile kernel.
+static bool lane_applies(const StepArgs& a, int dtype, int family, bool replay, bool accum, int flags) {
+    return !(flags & (KLHR_FIT_FORCE_OCTET | KLHR_FIT_FORCE_TILE)) && !replay && dtype == KLHR_F64 &&
+           family == KLHR_FAMILY_GAUSS && !accum && a.fp.or_K == 0 &&
+           (a.mp.id == KLHR_MODEL_NORMAL || a.mp.id == KLHR_MODEL_ILL_NORMAL) &&
+           lane_smem_bytes(a) + 1024 <= (size_t)(228 * 1024) / 4;
+}
+
 static bool tile_applies(const StepArgs& a, int family, bool accum, int flags) {
     // at most 2 stored direction-mean columns: they live in the tile's shared memory (J = 2 default)
     const int n_stored = a.dir.mean_cols ? a.dir.n_cols - a.dir.n_zero_cols : 0;
@@ -119,6 +130,7 @@ static int dispatch_chain(const StepArgs& a, int dtype, int family, bool replay,
 
 static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, bool accum, cudaStream_t st,
                          LaunchInfo* info, int flags) {
+    if (lane_applies(a, dtype, family, replay, accum, flags)) return launch_lane(a, st, info);
     if (tile_applies(a, family, accum, flags)) return launch_tile(a, dtype, replay, st, info);
     if (chain_applies(a, dtype, replay, accum, flags)) return dispatch_chain(a, dtype, family, replay, st, info);
     switch (a.mp.id) {

@@ -48,6 +48,7 @@ class FitConfig:
     c1: float = 1e-4
     basin: float = 1e-3
     force_octet: bool = False          # use the general octet kernel even where the tile kernel applies
+    force_tile: bool = False           # use the tile kernel even where the lane kernel applies
     x: np.ndarray = field(default=None, repr=False)
     w: np.ndarray = field(default=None, repr=False)
 
@@ -71,7 +72,7 @@ class FitConfig:
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin, flags=(1 if self.force_octet else 0) | (2 if self.fix_d else 0), kmax=int(self.kmax),
+                         basin=self.basin, flags=(1 if self.force_octet else 0) | (2 if self.fix_d else 0) | (4 if self.force_tile else 0), kmax=int(self.kmax),
                          overrelax_K=int(self.overrelax_K))
         for i in range(self.N):
             d.x[i] = float(self.x[i])
@@ -325,3 +326,31 @@ def launch_info(model: BSModel, fit: FitConfig, dtype=torch.float64, free_runnin
     if n <= 0:
         raise _lib.KLHRLibraryError(f"klhr_launch_info failed ({n}): {_lib.last_error()}")
     return dict(threads=t.value, smem=s.value, regs=r.value, ctas_per_sm=n)
+
+
+PROBE_KINDS = {"fp64_fma": 0, "normals": 1, "fp32_fma": 2, "cvt_f64_f32": 3, "mufu": 4, "mul_wide_u32": 5,
+               "f2d_int_pipe": 6, "fp64_dmma": 7}
+
+
+def peak_probe(kind, device, iters=4096, ctas_per_sm=8, repeats=5):
+    """Operations per second of one peak micro-kernel (``klhr_peak_probe``, csrc/klhr_probe.cu), best of
+    ``repeats`` launches timed with CUDA events on the current stream.  For "fp64_fma"/"fp32_fma" one operation
+    is one FMA (2 flop); for "normals" one standard normal of the step kernels' direction stream."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    ctas = torch.cuda.get_device_properties(dev).multi_processor_count * int(ctas_per_sm)
+    best = 0.0
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for r in range(repeats + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops = lib.klhr_peak_probe(PROBE_KINDS[kind], int(iters), ctas, out.data_ptr(), st)
+            e1.record()
+            if ops < 0:
+                raise _lib.KLHRLibraryError(f"klhr_peak_probe failed ({ops})")
+            torch.cuda.synchronize(dev)
+            if r > 0:                                   # first launch: module load + clock ramp
+                best = max(best, ops / (e0.elapsed_time(e1) * 1e-3))
+    return best

@@ -222,14 +222,54 @@ class KLHR(MCMCBase):
         self._advance(1)
         return self.theta
 
-    def sample(self, M, thin=1):
-        """``M`` rows, row 0 the current state (mcmc.py:31-37); ``thin`` keeps every thin-th draw."""
-        out = torch.empty(M, self.chains, self.D, dtype=self.dtype, device=self.device)
-        out[0] = self._theta
-        if M > 1:
-            self._advance((M - 1) * thin, draws=out[1:], thin=thin)
-        if self.chains == 1:
-            return out[:, 0].double().cpu().numpy()
+    def sample(self, M, thin=1, out=None, chunk_rows=None):
+        """``M`` rows, row 0 the current state (mcmc.py:31-37); ``thin`` keeps every thin-th draw.
+
+        ``out``: a pinned host tensor (M, chains, D) of the sampler's dtype.  The rows are then streamed to it while
+        the chains keep running: the kernel writes chunk k of ``chunk_rows`` rows into one of two device buffers
+        while chunk k-1 travels device -> host on a copy stream, so the device never holds more than two chunks
+        (at 65 536 chains x D = 100 x fp64 one row is 52 MB and PCIe, not the kernel, sets the pace)."""
+        if out is None:
+            dev_out = torch.empty(M, self.chains, self.D, dtype=self.dtype, device=self.device)
+            dev_out[0] = self._theta
+            if M > 1:
+                self._advance((M - 1) * thin, draws=dev_out[1:], thin=thin)
+            if self.chains == 1:
+                return dev_out[:, 0].double().cpu().numpy()
+            return dev_out
+        if (tuple(out.shape) != (M, self.chains, self.D) or out.dtype != self.dtype or out.is_cuda
+                or not out.is_pinned() or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous pinned host tensor of shape (M, chains, D) and the sampler's dtype")
+        row_bytes = self.chains * self.D * out.element_size()
+        chunk = int(chunk_rows) if chunk_rows else max(1, min(M, (128 << 20) // row_bytes))
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        bufs = [torch.empty(chunk, self.chains, self.D, dtype=self.dtype, device=self.device) for _ in range(2)]
+        freed = [None, None]
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            out[0].copy_(self._theta, non_blocking=True)
+            first = torch.cuda.Event()
+            first.record(cs)
+        cur.wait_event(first)                                        # row 0 is read before the state moves on
+        for k, r0 in enumerate(range(1, M, chunk)):
+            n = min(chunk, M - r0)
+            buf = bufs[k % 2]
+            if freed[k % 2] is not None:
+                cur.wait_event(freed[k % 2])                         # its previous content has reached the host
+            self._advance(n * thin, draws=buf[:n], thin=thin)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(cs):
+                cs.wait_event(done)
+                out[r0:r0 + n].copy_(buf[:n], non_blocking=True)
+                freed[k % 2] = torch.cuda.Event()
+                freed[k % 2].record(cs)
+        cs.synchronize()
         return out
 
     def run(self, n, chain_stats=False):

@@ -14,9 +14,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, direction=None, force_octet=False):
+    """``force_octet``: False (fastest applicable kernel: lane / tile / chain), True (octet kernel) or "tile"
+    (the tile kernel where the lane kernel would be chosen)."""
     model = kb.BSModel(stan_file=f"stan/{model_name}.stan", data=data, device=device())
     kfit, ofit = fit_pair(family, dtype)
-    kfit.force_octet = force_octet
+    kfit.force_octet = force_octet is True
+    kfit.force_tile = force_octet == "tile"
     D = model.dim()
     rng = np.random.default_rng(seed)
     theta0 = rng.normal(size=(B, D)) * 0.3
@@ -29,7 +32,9 @@ def _trace_run(model_name, data, family, B, S, seed=7, dtype=torch.float64, dire
 
 @pytest.mark.parametrize("model_name,data,family,force_octet", [
     ("ill-normal", {"D": 100}, "gauss", False), ("ill-normal", {"D": 100}, "gauss", True),
-    ("normal", {"D": 240}, "gauss", False), ("normal", {"D": 5}, "gauss", False),
+    ("ill-normal", {"D": 100}, "gauss", "tile"), ("ill-normal", {"D": 37}, "gauss", False),
+    ("normal", {"D": 240}, "gauss", False), ("normal", {"D": 5}, "gauss", False), ("normal", {"D": 5}, "gauss", "tile"),
+    ("normal", {"D": 2}, "gauss", False), ("ill-normal", {"D": 129}, "gauss", False),
     ("ill-normal", {"D": 1500}, "gauss", False),                  # large D: octet kernel, 64-thread CTAs
     ("funnel", {"D": 4}, "gauss", False), ("funnel", {"D": 4}, "gauss", True),
     ("funnel", {"D": 1}, "sinh", False), ("funnel", {"D": 1}, "sinh", True),
@@ -92,12 +97,13 @@ def test_philox_streams_are_standard_and_reproducible():
         kb.run(model, kfit, hi, 1, 11, chain_offset=1000, draw_offset=t)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat([lo, hi]), th_a)
-    # the octet kernel draws the same streams as the tile kernel (same chains up to round-off)
-    kfit.force_octet = True
-    oc = up(theta0)
-    kb.run(model, kfit, oc, S, 11)
-    torch.cuda.synchronize()
-    assert torch.allclose(oc, th_a, rtol=1e-9, atol=1e-9)
+    # the octet and tile kernels draw the same streams as the lane kernel (same chains up to round-off)
+    for octet, tile in ((True, False), (False, True)):
+        kfit.force_octet, kfit.force_tile = octet, tile
+        oc = up(theta0)
+        kb.run(model, kfit, oc, S, 11)
+        torch.cuda.synchronize()
+        assert torch.allclose(oc, th_a, rtol=1e-9, atol=1e-9)
 
 
 @pytest.mark.parametrize("model_name,data,family,force_octet", [
@@ -160,14 +166,14 @@ def test_direction_law_columns_and_kernel_agreement():
     p = np.array([0.5, 0.3, 0.2])
     direction = kb.Direction(mean_cols=up(e), sd=up(np.full(D, 1e-3)), cdf=up(np.cumsum(p)), n_zero_cols=1)
     rhos = []
-    for force in (False, True):
-        kfit.force_octet = force
+    for force in (False, True, "tile"):                    # lane, octet and tile kernels
+        kfit.force_octet, kfit.force_tile = force is True, force == "tile"
         th = up(np.zeros((B, D)))
         tr = kb.Trace(1, B, D, 2, torch.float64, device(), variates=True, rho=True)
         kb.run(model, kfit, th, 1, 99, direction, trace=tr)
         torch.cuda.synchronize()
         rhos.append(tr.rho[0].cpu().numpy())
-    assert np.allclose(rhos[0], rhos[1], rtol=1e-9, atol=1e-12)
+    assert np.allclose(rhos[0], rhos[1], rtol=1e-9, atol=1e-12) and np.allclose(rhos[0], rhos[2], rtol=1e-9, atol=1e-12)
     rho = rhos[0]
     assert np.allclose(np.linalg.norm(rho + 1e-12, axis=1), 1, atol=1e-10)
     f0 = (rho[:, 3] > 0.99).mean()
@@ -491,13 +497,15 @@ def test_device_exp_log_accuracy():
     assert np.array_equal(np.isnan(g), np.isnan(r)) and np.array_equal(g[~np.isnan(r)], r[~np.isnan(r)])
 
 
-def test_tile_kernel_thinned_draws_match_octet_kernel_and_states():
-    """sample(M, thin) on the tile kernel (pending moves applied on the fly): the rows are the chain states after
-    every thin-th draw -- equal to the octet kernel's rows up to round-off, across launch boundaries (adaptation
-    splits the run into launches of pca_stride draws) and for ragged batches."""
+@pytest.mark.parametrize("force_tile", [False, True])
+def test_tile_kernel_thinned_draws_match_octet_kernel_and_states(force_tile):
+    """sample(M, thin) on the lane / tile kernels (pending moves applied on the fly): the rows are the chain states
+    after every thin-th draw -- equal to the octet kernel's rows up to round-off, across launch boundaries
+    (adaptation splits the run into launches of pca_stride draws) and for ragged batches."""
     model = kb.BSModel(stan_file="stan/ill-normal.stan", data={"D": 100}, device=device())
     for B, thin, M, warm in ((1000, 1, 25, 0), (333, 3, 12, 0), (257, 4, 20, 40)):
         a = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
+        a._fit.force_tile = force_tile
         out_a = a.sample(M, thin=thin)
         b = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
         b._fit.force_octet = True
@@ -505,6 +513,7 @@ def test_tile_kernel_thinned_draws_match_octet_kernel_and_states():
         assert torch.allclose(out_a, out_b, rtol=1e-9, atol=1e-9)
         assert torch.equal(out_a[-1], a.theta)                       # last row = live state
         c = kb.KLHR(model, seed=9, chains=B, warmup=warm, windowsize=20)
+        c._fit.force_tile = force_tile
         c.run((M - 1) * thin)
         assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
         assert float((out_a[1:] != out_a[:-1]).any(dim=2).float().mean()) > 0.9    # acceptance ~ 1: rows move

@@ -15,16 +15,24 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--tag", default="")
 ap.add_argument("--octet", action="store_true")
+ap.add_argument("--tile", action="store_true", help="tile kernel where the lane kernel would be chosen")
+ap.add_argument("--peaks", action="store_true", help="print the peak micro-kernels (klhr_peak_probe) and exit")
 ap.add_argument("--slice", action="store_true", help="time klhr_slice_run instead of klhr_run")
 ap.add_argument("--direction", action="store_true", help="eigen_method_one law: 2 mean columns + zero column")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
+if a.peaks:
+    from klhr_b200 import engine
+    for k in engine.PROBE_KINDS:
+        print(f"peak {k:14s} {engine.peak_probe(k, dev):.4e} ops/s")
+    sys.exit(0)
 dt = torch.float64 if a.dtype == "f64" else torch.float32
 data = json.load(open(a.data[1:])) if a.data.startswith("@") else json.loads(a.data)
 model = kb.BSModel(stan_file=f"stan/{a.model}.stan", data=data, device=dev)
 base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32) if a.family == "sinh" else dict(family="gauss")
 fit = kb.FitConfig(**base).for_dtype(dt)
 fit.force_octet = a.octet
+fit.force_tile = a.tile
 D = model.dim()
 th = (torch.randn(a.chains, D, dtype=torch.float64, device=dev) * 0.5).to(dt).contiguous()
 acc = torch.zeros(a.chains, dtype=torch.int64, device=dev)
