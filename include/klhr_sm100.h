@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KLHR_ABI_VERSION 2
+#define KLHR_ABI_VERSION 3
 
 enum { KLHR_F64 = 0, KLHR_F32 = 1 };
 enum { KLHR_FAMILY_GAUSS = 0, KLHR_FAMILY_SINH = 1 };
@@ -84,6 +84,9 @@ typedef struct klhr_fit {
                                     search (1e-4: it only supplies the start of stage 2) and the inf-norm of the
                                     scaled KL gradient (1e-10)                                              */
     double step_cap, c1, basin;  /* Newton step cap, Armijo constant, full-step basin     */
+    double grad_clip;            /* sinh family: elementwise clip of the model gradient inside KL -- the reference's
+                                    KLHRSINH clips at its scale_clip (klhr_sinh.py:158-161), SUBKLHRSINH at its
+                                    grad_clip (sub_klhr_sinh.py:152-154); applied for dim <= 16; 0 = no clip    */
     double x[KLHR_MAX_NODES];    /* nodes  hermgauss(N).x * sqrt(2)   (klhr.py:46-48)      */
     double w[KLHR_MAX_NODES];    /* weights hermgauss(N).w / sqrt(pi) (klhr.py:49)         */
 } klhr_fit_t;
@@ -222,15 +225,24 @@ int klhr_math_eval(int op, const double* x_dev, double* y_dev, int64_t n, void* 
 
 /* Pooled second-moment accumulation for the adaptation PCA (replaces the per-sample CCIPCA
  * update onlinepca.py:13-26 with raw sums): outer[D][D] += sum_c (theta_c - shift)(theta_c - shift)^T,
- * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype. */
+ * s1[D] += sum_c (theta_c - shift).  fp64 accumulators regardless of dtype.
+ *   scratch_dev == NULL  the chain slices are combined straight into outer / s1 with fp64 atomics;
+ *   scratch_dev != NULL  (klhr_outer_scratch_doubles doubles, zeroed by the caller before the first call of a
+ *                        window) every slice of 1024 consecutive chains ADDS into its own plane of the scratch
+ *                        buffer and outer / s1 are not touched; klhr_outer_reduce folds the planes at the window
+ *                        closure.  Sums are then bit-reproducible and do not depend on how the chains are
+ *                        sharded over ranks (aligned power-of-two shards). */
 int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_dev, double* outer_dev,
                           double* s1_dev, int64_t n_chains, int32_t dim, double* scratch_dev,
                           int64_t scratch_doubles, void* stream);
 
-/* Size (in doubles) of the scratch buffer that makes klhr_outer_accumulate DETERMINISTIC: with it the chain
- * slices write partial planes that are added in a fixed order; with scratch_dev == NULL they are combined
- * with fp64 atomics (same value up to summation order). */
+/* Doubles of scratch for n_chains x dim: one (dim*dim + dim) plane per slice of 1024 chains. */
 int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim);
+
+/* outer[D][D] += tree-sum of the scratch planes' matrices, s1[D] += tree-sum of their first-moment rows (s1 may be
+ * NULL), with the canonical pairwise tree over the slice index; the planes are zeroed for the next window. */
+int klhr_outer_reduce(double* scratch_dev, int64_t scratch_doubles, double* outer_dev, double* s1_dev,
+                      int64_t n_chains, int32_t dim, void* stream);
 
 /* Occupancy query used by bench.py: threads per CTA and dynamic shared bytes the step
  * kernel would be launched with for this problem; returns resident CTAs per SM (<=0 error). */

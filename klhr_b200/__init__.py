@@ -8,9 +8,9 @@ CPU fallback.
 """
 from .bsmodel import BSModel
 from .engine import (FitConfig, Direction, Trace, SliceConfig, step_replay, run, slice_replay, slice_run, kl_eval,
-                     outer_accumulate, outer_scratch, launch_info, gauss_hermite)
+                     outer_accumulate, outer_scratch, outer_reduce, launch_info, gauss_hermite)
 
-__all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "outer_accumulate", "outer_scratch",
+__all__ = ["BSModel", "FitConfig", "Direction", "Trace", "step_replay", "run", "outer_accumulate", "outer_scratch", "outer_reduce",
            "launch_info", "gauss_hermite", "SliceConfig", "slice_replay", "slice_run", "kl_eval"]
 
 try:  # samplers (import kept soft only so that partial checkouts still expose the engine)

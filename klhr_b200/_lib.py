@@ -16,7 +16,7 @@ LIB_PATH = _HERE / "libklhr_sm100.so"
 KLHR_F64, KLHR_F32 = 0, 1
 FAMILY_GAUSS, FAMILY_SINH = 0, 1
 MAX_NODES = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MODEL_IDS = {"normal": 0, "ill-normal": 1, "funnel": 2, "corr-normal": 3, "ar1": 4, "arK": 5,
              "rosenbrock": 6, "earnings": 7}
@@ -32,7 +32,7 @@ class FitDesc(C.Structure):
                 ("nb", C.c_int32), ("flags", C.c_int32), ("kmax", C.c_int32), ("overrelax_K", C.c_int32),
                 ("initscale", C.c_double), ("tol", C.c_double), ("scale_clip", C.c_double),
                 ("gtol1", C.c_double), ("gtol2", C.c_double),
-                ("step_cap", C.c_double), ("c1", C.c_double), ("basin", C.c_double),
+                ("step_cap", C.c_double), ("c1", C.c_double), ("basin", C.c_double), ("grad_clip", C.c_double),
                 ("x", C.c_double * MAX_NODES), ("w", C.c_double * MAX_NODES)]
 
 
@@ -85,6 +85,7 @@ EXPORTS = {
     "klhr_outer_accumulate": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_outer_scratch_doubles": (C.c_int64, [C.c_int64, C.c_int32]),
+    "klhr_outer_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "klhr_philox_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_peak_probe": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "klhr_launch_info": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(FitDesc), C.c_int, C.c_int, C.c_int,

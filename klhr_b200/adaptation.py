@@ -4,9 +4,9 @@ The reference adapts ONE chain over time with three helpers used only by the sam
 ``WindowedAdaptation`` (windowedadaptation.py:1-43), ``OnlineMoments``
 (onlinemoments.py:3-28) and ``OnlinePCA`` (onlinepca.py:3-39).  The same three names and
 methods exist here, but every ``update`` consumes a whole batch of chains and stores RAW
-SUMS so that partial results merge exactly across CTAs, launches and ranks: one
-``all_reduce(SUM)`` of a flat fp64 buffer per window closure is the only collective of the
-whole sampler.
+SUMS so that partial results merge exactly across CTAs, launches and ranks: one collective
+on a flat fp64 buffer per window closure (an all-gather whose rows are then added in a
+canonical tree order) is the only communication of the whole sampler.
 
 CCIPCA is order dependent and cannot be pooled; ``OnlinePCA`` here keeps the second-moment
 matrix sum (x x^T) of the same centred inputs the reference feeds to CCIPCA
@@ -194,10 +194,25 @@ class Smoother:
         self._x = self._initial
 
 
+def _tree_sum(rows):
+    """Canonical pairwise tree over the rank index: ((r0 + r1) + (r2 + r3)) + ... -- the continuation of the tree
+    the kernels use over chain slices (csrc/klhr_api.cu:outer_reduce_kernel), so that equal power-of-two shards
+    reproduce the single-process sums bit for bit."""
+    rows = list(rows)
+    while len(rows) > 1:
+        nxt = [rows[i] + rows[i + 1] for i in range(0, len(rows) - 1, 2)]
+        if len(rows) % 2:
+            nxt.append(rows[-1])
+        rows = nxt
+    return rows[0]
+
+
 def allreduce_adaptation(moments, pca, group=None, extra=()):
-    """Sum the raw adaptation state over all ranks with ONE all_reduce of a flat fp64 buffer:
-    [N_moments, n_pca, s1 (D), s2 (D), outer (D*D), extra...].  No-op without an initialised
-    process group or with world size 1."""
+    """Sum the raw adaptation state over all ranks: ONE collective per window closure on a flat fp64 buffer
+    [N_moments, n_pca, s1 (D), s2 (D), outer (D*D), extra...].  The buffer is all-gathered and the ranks' rows are
+    added in a canonical tree order on every rank (identical bits everywhere, and identical to the single-process
+    sums for aligned power-of-two shards); NCCL's own all-reduce leaves the order of the additions unspecified.
+    No-op without an initialised process group or with world size 1.  ``extra`` tensors are summed in place too."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     parts = []
@@ -206,14 +221,17 @@ def allreduce_adaptation(moments, pca, group=None, extra=()):
     parts += [pca.outer.reshape(-1)] + [e.reshape(-1) for e in extra]
     dev = parts[0].device
     counts = torch.tensor([float(m.N) for m in moments] + [float(pca.n)], dtype=torch.float64, device=dev)
-    flat = torch.cat([counts] + parts)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat = torch.cat([counts] + [p_.to(torch.float64) for p_ in parts])
+    world = dist.get_world_size(group)
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat, group=group)
+    flat = _tree_sum(gathered)
     k = len(moments) + 1
     for i, mom in enumerate(moments):
         mom.N = int(round(float(flat[i])))
     pca.n = int(round(float(flat[len(moments)])))
-    for p in parts:
-        n = p.numel()
-        p.copy_(flat[k:k + n].reshape(p.shape))
+    for p_ in parts:
+        n = p_.numel()
+        p_.copy_(flat[k:k + n].reshape(p_.shape))
         k += n
     pca._eig = None

@@ -76,6 +76,8 @@ static int check_fit(const klhr_fit_t* f, FitParams& fp) {
     fp.fix_d = (f->flags & KLHR_FIT_FIX_D) ? 1 : 0;
     fp.initscale = f->initscale; fp.tol = f->tol; fp.scale_clip = f->scale_clip;
     fp.gtol1 = f->gtol1; fp.gtol2 = f->gtol2; fp.step_cap = f->step_cap; fp.c1 = f->c1; fp.basin = f->basin;
+    if (f->grad_clip < 0) return fail(-8, "grad_clip must be >= 0 (0 = no clip)");
+    fp.grad_clip = f->grad_clip;
     for (int i = 0; i < kMaxNodes; ++i) {
         fp.x[i] = i < f->n_nodes ? f->x[i] : 0.0;
         fp.w[i] = i < f->n_nodes ? f->w[i] : 0.0;
@@ -205,10 +207,11 @@ __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta,
             const int i = ti + 8 * fm + r8, j = tj + 8 * (fn + q) + 2 * k4 + e;
             if (i < D && j < D) {
                 if (plane) {
-                    // deterministic mode: every chain slice writes its partial tile to its own scratch plane
-                    // [slice][D*D + D]; outer_reduce_kernel adds the planes in a fixed order
-                    plane[(size_t)i * D + j] = acc[q][e];
-                    if (ti != tj) plane[(size_t)j * D + i] = acc[q][e];
+                    // deterministic mode: every chain slice ADDS its partial tile to its own scratch plane
+                    // [slice][D*D + D] (one owner thread per entry); klhr_outer_reduce folds the planes with a
+                    // canonical tree at the window closure
+                    plane[(size_t)i * D + j] += acc[q][e];
+                    if (ti != tj) plane[(size_t)j * D + i] += acc[q][e];
                 } else {
                     atomicAdd(outer + (size_t)i * D + j, acc[q][e]);
                     if (ti != tj) atomicAdd(outer + (size_t)j * D + i, acc[q][e]);
@@ -216,18 +219,34 @@ __global__ void __launch_bounds__(256) outer_kernel(const R* __restrict__ theta,
             }
         }
     if (blockIdx.y == blockIdx.x && ty == 0 && ti + tx < D) {
-        if (plane) plane[(size_t)D * D + ti + tx] = colsum;
+        if (plane) plane[(size_t)D * D + ti + tx] += colsum;
         else if (s1) atomicAdd(s1 + ti + tx, colsum);
     }
 }
 
-__global__ void outer_reduce_kernel(const double* __restrict__ scratch, double* __restrict__ outer,
+// Adds the per-slice planes with a CANONICAL pairwise tree over the slice index (slice = 1024 consecutive chains):
+// (((p0 + p1) + (p2 + p3)) + ...).  The tree of an aligned power-of-two run of slices is a subtree of the tree
+// of the whole range, so ranks that own such runs and combine their results pairwise in rank order
+// (adaptation.allreduce_adaptation) reproduce the single-process sum BIT FOR BIT.
+__global__ void outer_reduce_kernel(double* __restrict__ scratch, double* __restrict__ outer,
                                     double* __restrict__ s1, int D, int slices) {
     const size_t plane = (size_t)D * D + D;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane) return;
+    double stack[32];                       // stack[k]: sum of a complete aligned run of 2^k slices
+    int n = 0;                              // slices consumed; bit k of n <=> stack[k] is occupied
+    for (int s = 0; s < slices; ++s) {
+        double v = scratch[(size_t)s * plane + idx];
+        scratch[(size_t)s * plane + idx] = 0.0;          // ready for the next window
+        int k = 0;
+        while ((n >> k) & 1) { v = stack[k] + v; ++k; }
+        stack[k] = v;
+        ++n;
+    }
     double t = 0;
-    for (int s = 0; s < slices; ++s) t += scratch[(size_t)s * plane + idx];      // fixed order
+    bool have = false;
+    for (int k = 0; k < 32; ++k)            // ragged tail: fold the remaining runs from the smallest up
+        if ((n >> k) & 1) { t = have ? stack[k] + t : stack[k]; have = true; }
     if (idx < (size_t)D * D) outer[idx] += t;
     else if (s1) s1[idx - (size_t)D * D] += t;
 }
@@ -513,17 +532,13 @@ int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype
     return li.ctas_per_sm;
 }
 
-// chain slices of the SYRK: enough to fill the machine (~148 SMs * 4 CTAs over the upper-triangle tiles)
+// chain slices of the SYRK: 1024 consecutive chains each, whatever the batch size -- the canonical blocks of the
+// bit-reproducible, sharding-invariant reduction (outer_reduce_kernel)
 static void outer_slicing(int64_t n_chains, int32_t dim, int& tiles, long long& slices, long long& per) {
     tiles = (dim + 31) / 32;
-    const int tri = tiles * (tiles + 1) / 2;
-    slices = (592 + tri - 1) / tri;
-    const long long max_slices = (n_chains + 255) / 256;
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    per = (n_chains + slices - 1) / slices;
-    per = ((per + 31) / 32) * 32;
+    per = 1024;
     slices = (n_chains + per - 1) / per;
+    if (slices < 1) slices = 1;
 }
 
 int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim) {
@@ -553,12 +568,21 @@ int klhr_outer_accumulate(int dtype, const void* theta_dev, const void* shift_de
     else
         outer_kernel<float><<<grid, 256, 0, st>>>((const float*)theta_dev, (const float*)shift_dev, outer_dev,
                                                   s1_dev, n_chains, dim, (int)per, scratch_dev);
-    if (scratch_dev) {
-        const size_t plane = (size_t)dim * dim + dim;
-        outer_reduce_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(scratch_dev, outer_dev, s1_dev, dim,
-                                                                             (int)slices);
-    }
     return cuda_fail((int)cudaGetLastError(), "klhr_outer_accumulate");
+}
+
+int klhr_outer_reduce(double* scratch_dev, int64_t scratch_doubles, double* outer_dev, double* s1_dev,
+                      int64_t n_chains, int32_t dim, void* stream) {
+    if (!scratch_dev || !outer_dev) return fail(-1, "scratch and outer must not be NULL");
+    if (n_chains <= 0 || dim <= 0) return fail(-10, "bad sizes");
+    int tiles;
+    long long slices, per;
+    outer_slicing(n_chains, dim, tiles, slices, per);
+    const size_t plane = (size_t)dim * dim + dim;
+    if (scratch_doubles < (int64_t)(slices * (long long)plane)) return fail(-15, "scratch too small: see klhr_outer_scratch_doubles");
+    outer_reduce_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, (cudaStream_t)stream>>>(scratch_dev, outer_dev, s1_dev, dim,
+                                                                                         (int)slices);
+    return cuda_fail((int)cudaGetLastError(), "klhr_outer_reduce");
 }
 
 }  // extern "C"

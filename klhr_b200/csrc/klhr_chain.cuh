@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
                     oc.k0 = (uint32_t)a.seed; oc.k1d = (uint32_t)(a.seed >> 32) ^ (uint32_t)(odraw >> 32);
                 }
             }
-            fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so, oc);
+            // sinh family: elementwise gradient clip of klhr_sinh.py:158-161 (theta row: global memory, already
+            // carrying the previous draw's move; rho row: this chain's slot of the warp tile)
+            const ClipCtx<R> cc = clip_ctx<R>(a.fp, a.mp, D, g_theta + c_own * D, rho_all + (size_t)(4 * j + o) * Dp);
+            fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so, oc, cc);
             if (!kReplay && oc.K > 0 && a.tr.or_r) {
                 a.tr.or_r[(long long)step * a.B + c_own] = oc.r;
                 reinterpret_cast<R*>(a.tr.or_v)[(long long)step * a.B + c_own] = oc.v;

@@ -30,6 +30,13 @@ __device__ __forceinline__ R oct_sum(R v, unsigned m) {
     return v;
 }
 
+// sum over the G lanes that cooperate on one chain: G = 8 an octet, G = 1 a single thread (no shuffle)
+template <int G, typename R>
+__device__ __forceinline__ R grp_sum(R v, unsigned m) {
+    if constexpr (G == kOct) return oct_sum(v, m);
+    else return v;
+}
+
 // broadcast from lane `src` (0..7) of this octet
 template <typename R>
 __device__ __forceinline__ R oct_bcast(R v, int src, unsigned m) {
@@ -87,6 +94,53 @@ __device__ __forceinline__ Jet<R> jet_guard(R l, R l1, R l2) {
     j.l1 = ok ? l1 : R(0);
     j.l2 = ok ? l2 : R(0);
     return j;
+}
+
+// ------------------------------------------------------------------ elementwise gradient clip (sinh family)
+struct ModelParams;
+constexpr int kClipMaxD = 16;
+
+template <typename R>
+struct ClipCtx {
+    R c;                     // clip threshold; <= 0: off
+    const R* th;             // theta row of the chain (shared or global memory)
+    const R* rh;             // rho row
+    const ModelParams* mp;
+    int D;
+    __device__ __forceinline__ bool on() const { return c > R(0); }
+};
+
+template <typename R>
+__device__ __forceinline__ ClipCtx<R> clip_off() {
+    ClipCtx<R> cc;
+    cc.c = R(0); cc.th = nullptr; cc.rh = nullptr; cc.mp = nullptr; cc.D = 0;
+    return cc;
+}
+
+template <typename R, typename Model>
+__device__ __noinline__ R clip_l1_slow(R y, R l1, const ClipCtx<R>& cc) {
+    R pt[kClipMaxD], g[kClipMaxD];
+    for (int i = 0; i < cc.D; ++i) pt[i] = cc.th[i] + y * cc.rh[i];
+    Model::template lp_grad<1>(pt, g, 0, 0u, *cc.mp);
+    bool any = false;
+    R acc = 0;
+    for (int i = 0; i < cc.D; ++i) {
+        const R gi = g[i];
+        const R ci = r_clamp(gi, -cc.c, cc.c);
+        any = any || (ci != gi);
+        acc += ci * cc.rh[i];
+    }
+    return any ? acc : l1;
+}
+
+// default Model::eval_clip: full gradient wherever the evaluation is finite (models with a cheap test for "no
+// component can exceed c" specialise it, see Funnel)
+template <typename R, typename Model>
+__device__ __forceinline__ Jet<R> eval_clip_generic(const typename Model::Coef& cf, R y, const ClipCtx<R>& cc, R& l1c) {
+    const Jet<R> J = Model::eval(cf, y);
+    l1c = J.l1;
+    if (r_finite(J.l)) l1c = clip_l1_slow<R, Model>(y, J.l1, cc);
+    return J;
 }
 
 // ------------------------------------------------------------------ Philox4x32-10

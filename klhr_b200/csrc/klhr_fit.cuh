@@ -14,6 +14,7 @@
 #include "klhr_common.cuh"
 
 namespace klhr {
+struct ModelParams;
 
 struct FitParams {
     int family;            // KLHR_FAMILY_GAUSS | KLHR_FAMILY_SINH
@@ -24,16 +25,11 @@ struct FitParams {
     int fix_d;             // sinh family with d = 1 frozen (sub_klhr_sinh.py)
     double initscale, tol, scale_clip;
     double gtol1, gtol2, step_cap, c1, basin;
+    double grad_clip;      // > 0: elementwise clip of the model gradient inside the sinh-family KL (klhr_sinh.py:158-161)
     double x[kMaxNodes], w[kMaxNodes], cx[kMaxNodes];   // nodes, weights, asinh(nodes)
 };
 
 constexpr double kNewtonCapD = 64.0;
-
-template <int G, typename R>
-__device__ __forceinline__ R grp_sum(R v, unsigned m) {
-    if constexpr (G == kOct) return oct_sum(v, m);
-    else return v;
-}
 
 // ------------------------------------------------------------------ stage 1: 1-D mode search
 // A Newton step may be at most kNewtonCap trust radii long (oracle/batched.py:NEWTON_CAP): the candidates
@@ -225,6 +221,34 @@ __device__ void kl_gauss(const typename Model::Coef& cf, const R (&eta)[2], cons
     S.H[1][1] = -(S2xx * s2 + S1x * s);
 }
 
+// ------------------------------------------------------------------ elementwise gradient clip (sinh family)
+// The reference's KLHRSINH.KL projects np.clip(grad lp, -c, c) on rho (klhr_sinh.py:158-161,171-173) -- a clip of
+// every COMPONENT of the model gradient, which the O(1) line restriction cannot see.  Where Model::eval_mc says a
+// component may exceed c at theta + y rho, the full gradient is formed there by one thread (Model::lp_grad<1>,
+// D <= kClipMaxD) and l'(y) is replaced by sum_i clip(g_i) rho_i; evaluations on which nothing is clipped keep the
+// closed-form l'.  l'' (the Newton matrix) stays that of the unclipped density: same fixed points, and the
+// iteration is restated in oracle/batched.py with the same rule.
+// grad_clip applies to the sinh family only (klhr.py:106-120 does not clip) and to targets of at most kClipMaxD dims
+template <typename R>
+__device__ __forceinline__ ClipCtx<R> clip_ctx(const FitParams& fp, const ModelParams& mp, int D, const R* th, const R* rh) {
+    ClipCtx<R> cc = clip_off<R>();
+    if (fp.family == 1 && fp.grad_clip > 0.0 && fp.grad_clip < 1e300 && D <= kClipMaxD) {
+        cc.c = (R)fp.grad_clip; cc.th = th; cc.rh = rh; cc.mp = &mp; cc.D = D;
+    }
+    return cc;
+}
+
+// (jet, clipped l') of the line restriction at y
+template <typename R, typename Model>
+__device__ __forceinline__ Jet<R> eval_clipped(const typename Model::Coef& cf, R y, const ClipCtx<R>& cc, R& l1c) {
+    if (!cc.on()) {
+        const Jet<R> J = Model::eval(cf, y);
+        l1c = J.l1;
+        return J;
+    }
+    return Model::eval_clip(cf, y, cc, l1c);
+}
+
 // ------------------------------------------------------------------ sinh-arcsinh family
 template <typename R>
 struct SinhPar { R m, s, d, e; };
@@ -244,7 +268,7 @@ __device__ __forceinline__ SinhPar<R> sinh_unpack(const R (&eta)[4], const FitPa
 // (:146-156); second derivatives are those expressions differentiated once more.
 template <int G, typename R, typename Model>
 __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const FitParams& fp, int lane,
-                        unsigned m, KLState<R, 4>& S) {
+                        unsigned m, KLState<R, 4>& S, const ClipCtx<R>& cc) {
     const SinhPar<R> q = sinh_unpack<R>(eta, fp);
     const R c = (R)fp.scale_clip;
     const R invd = R(1) / q.d;
@@ -261,15 +285,16 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         const R th = sh / ch;
         const R sech2 = R(1) - th * th;
         const R T = q.m + q.s * sh;
-        const Jet<R> J = Model::eval(cf, T);
+        R l1c;                                                                    // l' with the elementwise clip
+        const Jet<R> J = eval_clipped<R, Model>(cf, T, cc, l1c);
         const R logJ = (eta[2] - eta[1]) - r_log(ch);
         f += w * (logJ - J.l);
         const R t1 = q.s * sh, t2 = -q.s * ch * a, t3 = q.s * ch * invd;          // grad T (t0 = 1)
         const R L2 = R(1) + th * a, L3 = -th * invd;                              // grad log|J| (L0 = 0, L1 = -1)
-        g0 += w * (-J.l1);
-        g1 += w * (-R(1) - J.l1 * t1);
-        g2 += w * (L2 - J.l1 * t2);
-        g3 += w * (L3 - J.l1 * t3);
+        g0 += w * (-l1c);
+        g1 += w * (-R(1) - l1c * t1);
+        g2 += w * (L2 - l1c * t2);
+        g3 += w * (L3 - l1c * t3);
         const R T11 = q.s * sh, T12 = -q.s * a * ch, T13 = q.s * ch * invd;
         const R T22 = q.s * a * ch + q.s * a * a * sh;
         const R T23 = -(q.s * invd) * (ch + a * sh);
@@ -281,12 +306,12 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         h01 += w * (-J.l2 * t1);
         h02 += w * (-J.l2 * t2);
         h03 += w * (-J.l2 * t3);
-        h11 += w * (-J.l2 * t1 * t1 - J.l1 * T11);
-        h12 += w * (-J.l2 * t1 * t2 - J.l1 * T12);
-        h13 += w * (-J.l2 * t1 * t3 - J.l1 * T13);
-        h22 += w * (L22 - J.l2 * t2 * t2 - J.l1 * T22);
-        h23 += w * (L23 - J.l2 * t2 * t3 - J.l1 * T23);
-        h33 += w * (L33 - J.l2 * t3 * t3 - J.l1 * T33);
+        h11 += w * (-J.l2 * t1 * t1 - l1c * T11);
+        h12 += w * (-J.l2 * t1 * t2 - l1c * T12);
+        h13 += w * (-J.l2 * t1 * t3 - l1c * T13);
+        h22 += w * (L22 - J.l2 * t2 * t2 - l1c * T22);
+        h23 += w * (L23 - J.l2 * t2 * t3 - l1c * T23);
+        h33 += w * (L33 - J.l2 * t3 * t3 - l1c * T33);
     }
     S.f = grp_sum<G>(f, m);
     g0 = grp_sum<G>(g0, m); g1 = grp_sum<G>(g1, m); g2 = grp_sum<G>(g2, m); g3 = grp_sum<G>(g3, m);
@@ -309,9 +334,9 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
 
 template <int G, typename R, typename Model, int n>
 __device__ __forceinline__ void kl_eval(const typename Model::Coef& cf, const R (&eta)[n], const FitParams& fp,
-                                        int lane, unsigned m, KLState<R, n>& S) {
+                                        int lane, unsigned m, KLState<R, n>& S, const ClipCtx<R>& cc) {
     if constexpr (n == 2) kl_gauss<G, R, Model>(cf, eta, fp, lane, m, S);
-    else kl_sinh<G, R, Model>(cf, eta, fp, lane, m, S);
+    else kl_sinh<G, R, Model>(cf, eta, fp, lane, m, S, cc);
 }
 
 template <typename R, int n>
@@ -330,7 +355,7 @@ __device__ __forceinline__ R scale_of(const R (&eta)[n], const FitParams& fp) {
 // with 4 octets (or 32 single-thread chains) per warp the nested form ran one group at a time.
 template <int G, typename R, typename Model, int n>
 __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
-                              unsigned m, int& nev, bool& converged, R& s_out) {
+                              unsigned m, int& nev, bool& converged, R& s_out, const ClipCtx<R>& cc) {
     const unsigned wm = __activemask();        // the lanes that entered together stay in lock-step
     KLState<R, n> S;
     R p[n], trial[n];
@@ -345,7 +370,7 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
     for (int k = 0; k < max_evals; ++k) {
         if (!__any_sync(wm, !done)) break;
         KLState<R, n> St;
-        kl_eval<G, R, Model, n>(cf, trial, fp, lane, m, St);
+        kl_eval<G, R, Model, n>(cf, trial, fp, lane, m, St, cc);
         if (!done) {
             nev += 1;
             bool accepted;
@@ -495,7 +520,8 @@ __device__ inline void overrelax_sample(OrCtx<R>& oc, R u0) {
 // (reference draw order: klhr.py:129,180,188 ; klhr_sinh.py:184,191,246,255).
 template <int G, typename R, typename Model, int n>
 __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams& fp, int lane, unsigned m,
-                                R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o, OrCtx<R>& oc) {
+                                R z_init, R init2, R init3, R z_prop, R u, StepOut<R>& o, OrCtx<R>& oc,
+                                const ClipCtx<R>& cc = clip_off<R>()) {
     R xi, tau0;
     int nev1, nev2;
     stage1_mode<G, R, Model>(cf, z_init, fp, lane, m, xi, tau0, nev1);
@@ -512,7 +538,7 @@ __device__ void fit_and_propose(const typename Model::Coef& cf, const FitParams&
     }
     bool conv;
     R s_fit;
-    stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv, s_fit);
+    stage2_newton<G, R, Model, n>(cf, eta, fp, lane, m, nev2, conv, s_fit, cc);
     R zp, lq0, lq1;
     if constexpr (n == 2) {
         const R s = s_fit;                          // = exp(clamp(eta[1])), klhr.py:81-85

@@ -18,6 +18,11 @@
 
 namespace klhr {
 
+#define KLHR_DEFAULT_EVAL_CLIP                                                                                       \
+    __device__ static __forceinline__ Jet<R> eval_clip(const Coef& c, R y, const ClipCtx<R>& cc, R& l1c) {             \
+        return eval_clip_generic<R, Self>(c, y, cc, l1c);                                                             \
+    }
+
 struct ModelParams {
     int id;            // KLHR_MODEL_*
     int D;             // model.dim()
@@ -47,6 +52,7 @@ __device__ __forceinline__ Jet<R> quad_eval(const QuadCoef<R>& c, R y) {
 // ---- stan/normal.stan:1-9 and stan/ill-normal.stan:1-12  (diagonal Gaussian)
 template <typename R, bool kScaled>
 struct DiagNormal {
+    using Self = DiagNormal<R, kScaled>;
     static constexpr bool kDenseCta = false;
     using Coef = QuadCoef<R>;
     __device__ static __forceinline__ R wgt(int i, const ModelParams& mp) {
@@ -65,20 +71,23 @@ struct DiagNormal {
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         R acc = 0;
-        for (int i = lane; i < mp.D; i += kOct) {
+        for (int i = lane; i < mp.D; i += G) {
             const R gi = -th[i] * wgt(i, mp);
             if (g) g[i] = gi;
             acc += th[i] * gi;
         }
-        return R(0.5) * oct_sum(acc, m);
+        return R(0.5) * grp_sum<G>(acc, m);
     }
 };
 
 // ---- stan/corr-normal.stan:1-20  (dense precision P = Sigma^-1, symmetric)
 template <typename R>
 struct CorrNormal {
+    using Self = CorrNormal<R>;
     static constexpr bool kDenseCta = true;     // fp64: CTA-cooperative DMMA path, klhr_dense.cuh
     using Coef = QuadCoef<R>;
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
@@ -97,23 +106,26 @@ struct CorrNormal {
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         const R* P = reinterpret_cast<const R*>(mp.p0);
         const int D = mp.D;
         R acc = 0;
-        for (int i = lane; i < D; i += kOct) {
+        for (int i = lane; i < D; i += G) {
             R v = 0;
             for (int k = 0; k < D; ++k) v += __ldg(P + (size_t)k * D + i) * th[k];
             if (g) g[i] = -v;
             acc -= th[i] * v;
         }
-        return R(0.5) * oct_sum(acc, m);
+        return R(0.5) * grp_sum<G>(acc, m);
     }
 };
 
 // ---- stan/ar1.stan:1-14   e_t(v) = v_t - alpha v_{t-1}
 template <typename R>
 struct AR1 {
+    using Self = AR1<R>;
     static constexpr bool kDenseCta = false;
     using Coef = QuadCoef<R>;
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
@@ -136,11 +148,13 @@ struct AR1 {
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         const R al = (R)mp.s0, ib2 = (R)mp.s1;
         const int D = mp.D;
         R acc = 0;
-        for (int i = lane; i < D; i += kOct) {
+        for (int i = lane; i < D; i += G) {
             R gi;
             if (i == 0) {
                 acc -= R(0.5) * th[0] * th[0];
@@ -153,15 +167,16 @@ struct AR1 {
             if (i + 1 < D) gi += ib2 * al * (th[i + 1] - al * th[i]);
             if (g) g[i] = gi;
         }
-        return oct_sum(acc, m);
+        return grp_sum<G>(acc, m);
     }
 };
 
 // ---- stan/funnel.stan:1-11   params [x, alpha_1..alpha_Da]
 template <typename R>
 struct Funnel {
+    using Self = Funnel<R>;
     static constexpr bool kDenseCta = false;
-    struct Coef { R x0, r0, a0, a1, a2, hd, l0; };
+    struct Coef { R x0, r0, a0, a1, a2, hd, l0, t1, r1; };     // t1, r1: first alpha and its direction (dims = 2 clip path)
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         R a0 = 0, a1 = 0, a2 = 0;
         for (int i = 1 + lane; i < mp.D; i += kOct) {
@@ -177,6 +192,8 @@ struct Funnel {
         c.x0 = th[0];
         c.r0 = rh[0];
         c.hd = R(0.5) * (R)mp.i0;
+        c.t1 = mp.D > 1 ? th[1] : R(0);
+        c.r1 = mp.D > 1 ? rh[1] : R(0);
         c.l0 = -c.x0 * c.x0 * R(1.0 / 18.0) - c.hd * c.x0 - R(0.5) * r_exp(-c.x0) * c.a0;
         return c;
     }
@@ -193,15 +210,58 @@ struct Funnel {
         const R l2 = -c.r0 * c.r0 * R(1.0 / 9.0) - R(0.5) * ex * (c.r0 * c.r0 * S - R(2) * c.r0 * S1 + S2);
         return jet_guard<R>(l, l1, l2);
     }
+    // eval + l' of the elementwise clipped gradient (klhr_sinh.py:158-161).  d/dx is formed exactly; the alpha
+    // components are -alpha_i e^-x, bounded together by e^-x sqrt(sum alpha^2): only when one of the two can
+    // exceed the clip are the components walked (theta / rho rows of the chain), sharing the exponential.
+    __device__ static __forceinline__ Jet<R> eval_clip(const Coef& c, R y, const ClipCtx<R>& cc, R& l1c) {
+        const R x = c.x0 + y * c.r0;
+        const R ex = r_exp(-x);
+        const R S = c.a0 + y * (R(2) * c.a1 + y * c.a2);
+        const R S1 = R(2) * (c.a1 + y * c.a2);
+        const R S2 = R(2) * c.a2;
+        const R l = -x * x * R(1.0 / 18.0) - c.hd * x - R(0.5) * ex * S - c.l0;
+        const R l1 = -c.r0 * x * R(1.0 / 9.0) - c.hd * c.r0 - R(0.5) * ex * (S1 - c.r0 * S);
+        const R l2 = -c.r0 * c.r0 * R(1.0 / 9.0) - R(0.5) * ex * (c.r0 * c.r0 * S - R(2) * c.r0 * S1 + S2);
+        const Jet<R> J = jet_guard<R>(l, l1, l2);
+        l1c = J.l1;
+        const R clip = cc.c;
+        const R gxa = -x * R(1.0 / 9.0) - c.hd + R(0.5) * ex * S;           // d/dx (reciprocal multiply)
+        if (cc.D == 2) {
+            // stan/funnel.json (one alpha): both components in closed form, no branch in the node loop
+            const R ga = -(c.t1 + y * c.r1) * ex;
+            const R cx = r_clamp(gxa, -clip, clip), ca = r_clamp(ga, -clip, clip);
+            const bool any = (cx != gxa) || (ca != ga);
+            const R acc = cx * c.r0 + ca * c.r1;
+            l1c = (any && r_finite(J.l)) ? acc : J.l1;
+            return J;
+        }
+        // more alphas: cheap guard with a 1 % margin; the components are walked only when it trips
+        const bool may = !(r_abs(gxa) < R(0.99) * clip) || !(ex * ex * S < R(0.98) * clip * clip);
+        if (may && r_finite(J.l)) {
+            const R gx = -x / R(9) - c.hd + R(0.5) * ex * S;                  // as lp_grad forms it
+            const R cx = r_clamp(gx, -clip, clip);
+            bool any = cx != gx;
+            R acc = cx * c.r0;
+            for (int i = 1; i < cc.D; ++i) {
+                const R gi = -(cc.th[i] + y * cc.rh[i]) * ex;
+                const R ci = r_clamp(gi, -clip, clip);
+                any = any || (ci != gi);
+                acc += ci * cc.rh[i];
+            }
+            if (any) l1c = acc;
+        }
+        return J;
+    }
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         const R x = th[0];
         const R ex = r_exp(-x);
         R ss = 0;
-        for (int i = 1 + lane; i < mp.D; i += kOct) {
+        for (int i = 1 + lane; i < mp.D; i += G) {
             ss += th[i] * th[i];
             if (g) g[i] = -th[i] * ex;
         }
-        ss = oct_sum(ss, m);
+        ss = grp_sum<G>(ss, m);
         const R hd = R(0.5) * (R)mp.i0;
         if (g && lane == 0) g[0] = -x / R(9) - hd + R(0.5) * ex * ss;
         return -x * x / R(18) - hd * x - R(0.5) * ex * ss;
@@ -211,6 +271,7 @@ struct Funnel {
 // ---- stan/rosenbrock.stan:1-12   params [v_1..v_Dh, t_1..t_Dh]
 template <typename R>
 struct Rosenbrock {
+    using Self = Rosenbrock<R>;
     static constexpr bool kDenseCta = false;
     struct Coef { R b1, b2, b3, b4; };      // l(y) - l(0) = b1 y + b2 y^2 + b3 y^3 + b4 y^4
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
@@ -241,10 +302,12 @@ struct Rosenbrock {
         const R l2 = R(2) * c.b2 + y * (R(6) * c.b3 + y * R(12) * c.b4);
         return jet_guard<R>(l, l1, l2);
     }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         const int Dh = mp.i0;
         R acc = 0;
-        for (int i = lane; i < Dh; i += kOct) {
+        for (int i = lane; i < Dh; i += G) {
             const R v = th[i], t = th[Dh + i];
             const R c = t - v * v;
             acc -= R(0.5) * (v - R(1)) * (v - R(1)) + R(50) * c * c;
@@ -253,7 +316,7 @@ struct Rosenbrock {
                 g[Dh + i] = -R(100) * c;
             }
         }
-        return oct_sum(acc, m);
+        return grp_sum<G>(acc, m);
     }
 };
 
@@ -262,8 +325,10 @@ struct Rosenbrock {
 // over t = K+1..T, packed [G (K+1)^2 | c (K+1) | yy].  sum r^2 = yy - 2 phi.c + phi^T G phi.
 template <typename R>
 struct ARK {
+    using Self = ARK<R>;
     static constexpr bool kDenseCta = false;
     struct Coef { R p0, p1, p2, q0, q1, q2, u0, ru, nm1, l0; };
+    template <int GS = kOct>
     __device__ static __forceinline__ void gram_forms(const R* th, const R* rh, int lane, unsigned m,
                                                       const ModelParams& mp, R& q0, R& q1, R& q2,
                                                       R& p0, R& p1, R& p2, R* gphi /*(G phi - c)_lane or null*/) {
@@ -276,7 +341,7 @@ struct ARK {
         const double yy = __ldg(cv + K1);
         double s_pc = 0, s_pGp = 0, s_rGp = 0, s_rGr = 0, s_rc = 0;
         R pp = 0, pr = 0, rr = 0;
-        for (int i = lane; i < K1; i += kOct) {
+        for (int i = lane; i < K1; i += GS) {
             double Gp = 0, Gr = 0;
             for (int k = 0; k < K1; ++k) {
                 const double gik = __ldg(G + i * K1 + k);
@@ -294,9 +359,9 @@ struct ARK {
             rr += rh[i] * rh[i];
             if (gphi) gphi[i] = (R)(Gp - ci);
         }
-        s_pc = oct_sum(s_pc, m); s_pGp = oct_sum(s_pGp, m); s_rGp = oct_sum(s_rGp, m);
-        s_rGr = oct_sum(s_rGr, m); s_rc = oct_sum(s_rc, m);
-        p0 = oct_sum(pp, m); p1 = oct_sum(pr, m); p2 = oct_sum(rr, m);
+        s_pc = grp_sum<GS>(s_pc, m); s_pGp = grp_sum<GS>(s_pGp, m); s_rGp = grp_sum<GS>(s_rGp, m);
+        s_rGr = grp_sum<GS>(s_rGr, m); s_rc = grp_sum<GS>(s_rc, m);
+        p0 = grp_sum<GS>(pp, m); p1 = grp_sum<GS>(pr, m); p2 = grp_sum<GS>(rr, m);
         q0 = (R)(yy - 2.0 * s_pc + s_pGp);      // sum r^2 at phi
         q1 = (R)(s_rGp - s_rc);                 // 1/2 d/dy sum r^2
         q2 = (R)s_rGr;
@@ -329,16 +394,18 @@ struct ARK {
                      - R(0.5) * em2 * (R(4) * c.ru * c.ru * S - R(4) * c.ru * S1 + S2);
         return jet_guard<R>(l, l1, l2);
     }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         // rho := theta is a harmless stand-in for the unused direction sums
         R q0, q1, q2, p0, p1, p2;
         const int K1 = mp.i0 + 1;
         const R u = th[mp.D - 1];
         const R e2 = r_exp(R(2) * u), em2 = r_exp(-R(2) * u);
-        gram_forms(th, th, lane, m, mp, q0, q1, q2, p0, p1, p2, g);
+        gram_forms<G>(th, th, lane, m, mp, q0, q1, q2, p0, p1, p2, g);
         // p0 counted the first K+1 entries only (phi); gphi holds (G phi - c)_i = -(X^T r)_i
         if (g) {
-            for (int i = lane; i < K1; i += kOct) g[i] = -th[i] - em2 * g[i];
+            for (int i = lane; i < K1; i += G) g[i] = -th[i] - em2 * g[i];
             if (lane == 0) g[mp.D - 1] = -e2 + R(1) - (R)mp.i1 + em2 * q0;
         }
         return -R(0.5) * p0 - R(0.5) * e2 + u - (R)mp.i1 * u - R(0.5) * em2 * q0;
@@ -351,6 +418,7 @@ struct ARK {
 // SSR(b) = See - 2 b1 Se - 2 b2 Seh + b1^2 N + 2 b1 b2 Sh + b2^2 Shh.
 template <typename R>
 struct Earnings {
+    using Self = Earnings<R>;
     static constexpr bool kDenseCta = false;
     struct Coef { R b1, b2, r1, r2, us0, rs, ut0, rt, S0, S1, S2, nm1, l0; };
     struct Stats { double N, Se, Sh, See, Seh, Shh; };        // always fp64 (dollar-scale sums)
@@ -413,6 +481,8 @@ struct Earnings {
         }
         return jet_guard<R>(l, l1, l2);
     }
+    KLHR_DEFAULT_EVAL_CLIP
+    template <int G = kOct>
     __device__ static R lp_grad(const R* th, R* g, int lane, unsigned m, const ModelParams& mp) {
         const Stats s = stats(mp);
         const R b1 = th[0], b2 = th[1], us = th[2], ut = th[3];

@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(kThreadsMax, step_min_ctas<R, Model>()) step_k
                     oc.k0 = (uint32_t)a.seed; oc.k1d = (uint32_t)(a.seed >> 32) ^ (uint32_t)(odraw >> 32);
                 }
             }
-            fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so, oc);
+            const ClipCtx<R> cc = clip_ctx<R>(a.fp, a.mp, D, th, rh);        // klhr_sinh.py:158-161 (sinh family only)
+            fit_and_propose<kOct, R, Model, NE>(cf, a.fp, lane, om, z_init, init2, init3, z_prop, u, so, oc, cc);
             if (!kReplay && oc.K > 0 && a.tr.or_r && lane == 0) {
                 a.tr.or_r[row] = oc.r;
                 reinterpret_cast<R*>(a.tr.or_v)[row] = oc.v;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kThreadsMax) kl_eval_kernel(const __grid_const
         const R clip = (R)a.fp.scale_clip;
         s = r_exp(r_clamp(eta[1], -clip, clip));
     } else {
-        kl_sinh<kOct, R, Model>(cf, eta, a.fp, lane, om, S);
+        kl_sinh<kOct, R, Model>(cf, eta, a.fp, lane, om, S, clip_ctx<R>(a.fp, a.mp, D, th, rh));
         s = sinh_unpack<R>(eta, a.fp).s;
     }
     if (lane != 0) return;

@@ -47,6 +47,7 @@ class FitConfig:
     step_cap: float = 2.0
     c1: float = 1e-4
     basin: float = 1e-3
+    grad_clip: float = 0.0             # sinh family: elementwise clip of the model gradient in KL (klhr_sinh.py:158-161); 0 = off
     force_octet: bool = False          # use the general octet kernel even where the tile kernel applies
     force_tile: bool = False           # use the tile kernel even where the lane kernel applies
     x: np.ndarray = field(default=None, repr=False)
@@ -63,16 +64,28 @@ class FitConfig:
     def for_dtype(self, dtype):
         """Convergence thresholds scaled to the arithmetic type."""
         if dtype == torch.float32:
-            return FitConfig(**{**self.__dict__, "gtol1": max(self.gtol1, 1e-4),
-                                "gtol2": max(self.gtol2, 2e-5)})
+            fields = {k: v for k, v in self.__dict__.items() if not k.startswith("_")}
+            return FitConfig(**{**fields, "gtol1": max(self.gtol1, 1e-4), "gtol2": max(self.gtol2, 2e-5)})
         return self
 
     def descriptor(self):
+        """``klhr_fit_t`` for the C ABI (cached: a sampler launches thousands of times with the same settings)."""
+        key = (self.family, self.N, self.initscale, self.tol, self.scale_clip, self.n1, self.n2, self.nb, self.kmax,
+               self.overrelax_K, self.fix_d, self.gtol1, self.gtol2, self.step_cap, self.c1, self.basin, self.grad_clip,
+               self.force_octet, self.force_tile, self.x.tobytes(), self.w.tobytes())
+        cached = self.__dict__.get("_desc_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        d = self._build_descriptor()
+        self.__dict__["_desc_cache"] = (key, d)
+        return d
+
+    def _build_descriptor(self):
         d = _lib.FitDesc(family=_lib.FAMILY_GAUSS if self.family == "gauss" else _lib.FAMILY_SINH,
                          n_nodes=self.N, n1=self.n1, n2=self.n2, nb=self.nb,
                          initscale=self.initscale, tol=self.tol, scale_clip=self.scale_clip,
                          gtol1=self.gtol1, gtol2=self.gtol2, step_cap=self.step_cap, c1=self.c1,
-                         basin=self.basin, flags=(1 if self.force_octet else 0) | (2 if self.fix_d else 0) | (4 if self.force_tile else 0), kmax=int(self.kmax),
+                         basin=self.basin, grad_clip=float(self.grad_clip), flags=(1 if self.force_octet else 0) | (2 if self.fix_d else 0) | (4 if self.force_tile else 0), kmax=int(self.kmax),
                          overrelax_K=int(self.overrelax_K))
         for i in range(self.N):
             d.x[i] = float(self.x[i])
@@ -292,16 +305,17 @@ def slice_run(model: BSModel, cfg: SliceConfig, theta, n_steps, seed, direction:
 
 
 def outer_scratch(theta):
-    """Scratch tensor that makes ``outer_accumulate`` deterministic for this (B, D)."""
+    """Zeroed scratch planes for ``outer_accumulate`` on this (B, D): one (D*D + D) plane per slice of 1024 chains."""
     B, D = theta.shape
     n = int(_lib.load().klhr_outer_scratch_doubles(B, D))
-    return torch.empty(max(n, 1), dtype=torch.float64, device=theta.device)
+    return torch.zeros(max(n, 1), dtype=torch.float64, device=theta.device)
 
 
 def outer_accumulate(theta, shift, outer, s1=None, scratch=None):
-    """outer (D, D) += sum_c (theta_c - shift)(theta_c - shift)^T ; s1 (D,) += sum_c (theta_c - shift).
-    With ``scratch`` (``outer_scratch(theta)``) the chain slices are combined in a fixed order (bit-reproducible);
-    without it they are combined with fp64 atomics."""
+    """Pooled second moments of (theta - shift).  Without ``scratch``: outer (D, D) += sum_c u_c u_c^T and
+    s1 (D,) += sum_c u_c, combined with fp64 atomics.  With ``scratch`` (``outer_scratch(theta)``): every slice of
+    1024 chains adds into its own scratch plane and ``outer`` / ``s1`` are left alone until ``outer_reduce`` folds
+    the planes (bit-reproducible and independent of the sharding of the chains over ranks)."""
     lib = _lib.load()
     _require_cuda(theta, "theta")
     B, D = theta.shape
@@ -311,6 +325,15 @@ def outer_accumulate(theta, shift, outer, s1=None, scratch=None):
                                              outer.data_ptr(), _ptr(s1), B, D, _ptr(scratch),
                                              scratch.numel() if scratch is not None else 0, st),
                    "klhr_outer_accumulate")
+
+
+def outer_reduce(scratch, outer, s1, B, D):
+    """outer += tree-sum of the scratch planes, s1 += tree-sum of their first-moment rows; zeroes the planes."""
+    lib = _lib.load()
+    with torch.cuda.device(outer.device):
+        st = torch.cuda.current_stream(outer.device).cuda_stream
+        _lib.check(lib.klhr_outer_reduce(scratch.data_ptr(), scratch.numel(), outer.data_ptr(), _ptr(s1), int(B), int(D), st),
+                   "klhr_outer_reduce")
 
 
 def launch_info(model: BSModel, fit: FitConfig, dtype=torch.float64, free_running=True, accumulate=False,

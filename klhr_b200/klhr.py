@@ -39,7 +39,7 @@ class KLHR(MCMCBase):
                  windowsize=50, windowscale=2, tol=1e-12, grad_clip=1e15, scale_clip=600,
                  scale_dir_cov=False, overrelaxed=False, eigen_method_one=True, max_init_tries=100, *,
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
-                 pca_stride=10, moments_every_draw=False, fit_budget=None):
+                 pca_stride=None, moments_every_draw=False, fit_budget=None):
         super().__init__(bsmodel, -1, theta=theta, seed=seed, chains=chains, dtype=dtype, device=device)
         if not 1 <= int(K) <= 50:
             raise ValueError("K must be in 1..50 (the reference clips it there, klhr.py:213)")
@@ -55,12 +55,16 @@ class KLHR(MCMCBase):
                                      **{"n2": 24 if self._family == "gauss" else 48,
                                         "kmax": 0 if self._family == "gauss" else 32, **budget}).for_dtype(dtype)
         self._fit.overrelax_K = self.K if overrelaxed else 0       # klhr.py:160-173 / klhr_sinh.py:215-228
+        self._fit.grad_clip = self._kl_grad_clip()
         self._smoothK = Smoother(self.K)
         self._windowedadaptation = WindowedAdaptation(warmup, windowsize=windowsize, windowscale=windowscale)
         self._scale_dir_cov = scale_dir_cov
         self._overrelaxed = overrelaxed
         self._eigen_method_one = eigen_method_one
-        self._pca_stride = max(1, int(pca_stride))
+        # snapshots of the ensemble that feed the window moments / PCA sums: every `pca_stride` draws, or (None) as
+        # sparse as keeps >= ~2048 pooled samples and >= 4 snapshots per window -- one chain: every draw, like the
+        # reference's per-draw update (klhr.py:216-218); 65 536 chains: 4 per window
+        self._pca_stride = None if pca_stride is None else max(1, int(pca_stride))
         # False (default): the window moments come from the same ensemble snapshots as the PCA sums
         # (every pca_stride draws, all chains) and the warm-up runs on the fast kernels; True: every
         # non-closure draw of every chain is accumulated in-kernel like klhr.py:216-218 does per draw
@@ -78,6 +82,7 @@ class KLHR(MCMCBase):
         self._draw = 0
         self._outer_scratch = None
         self._acc_seen = 0.0
+        self._smooth_log = []                      # (accepted draws of this rank, steps, smoother updates) per launch
         self._accept_count = torch.zeros(self.chains, dtype=torch.int64, device=dev)
         self._evals_total = torch.zeros(1, dtype=torch.int64, device=dev)
         if chain_offset is None:
@@ -92,26 +97,37 @@ class KLHR(MCMCBase):
             self._initialize()
 
     # ------------------------------------------------------------------ reference quirks kept per class
+    def _kl_grad_clip(self):
+        """Elementwise clip of the model gradient inside ``KL``: none in KLHR (klhr.py:106-120 calls the model
+        directly; ``_logp_grad`` :101-104 is unused)."""
+        return 0.0
+
     def _clip_J(self, J):
         return J if J < self.D else self.D - 1                 # klhr.py:39
 
     # ------------------------------------------------------------------ start points (klhr.py:87-99)
     def _initialize(self):
-        g = torch.Generator(device="cpu").manual_seed(self.seed)
-        todo = torch.ones(self.chains, dtype=torch.bool, device=self.device)
-        for _ in range(self._max_init_tries):
-            n = int(todo.sum())
-            if n == 0:
-                return
-            cand = (torch.randn(n, self.D, generator=g, dtype=torch.float64) * self._initscale)
-            cand = cand.to(self.device, self.dtype)
-            lp, grad = self.model.log_density_gradient(cand)
-            ok = torch.isfinite(lp) & torch.isfinite(grad.norm(dim=1))
-            idx = todo.nonzero().squeeze(1)
-            self._theta[idx[ok]] = cand[ok]
-            todo[idx[ok]] = False
-        if bool(todo.any()):
-            raise RuntimeError("failed to initialize")
+        """Random finite start per chain (klhr.py:87-99: N(0, initscale^2), retried until lp and the gradient are
+        finite).  Chain c's start is a function of (seed, chain_offset + c) only -- blocks of 4096 global chain ids
+        own one generator each -- so a sharded run starts exactly where the unsharded one does."""
+        blk = 4096
+        lo, hi = self._chain_offset, self._chain_offset + self.chains
+        for b in range(lo // blk, (hi - 1) // blk + 1):
+            g = torch.Generator(device="cpu").manual_seed((self.seed * 0x9E3779B97F4A7C15 + b * 0xD1B54A32D192ED03 + 1) % (1 << 63))
+            a, z = max(lo, b * blk), min(hi, (b + 1) * blk)
+            sl = slice(a - lo, z - lo)
+            todo = torch.ones(z - a, dtype=torch.bool, device=self.device)
+            for _ in range(self._max_init_tries):
+                if not bool(todo.any()):
+                    break
+                cand = (torch.randn(blk, self.D, generator=g, dtype=torch.float64) * self._initscale)[a - b * blk:z - b * blk]
+                cand = cand.to(self.device, self.dtype)
+                lp, grad = self.model.log_density_gradient(cand)
+                ok = todo & torch.isfinite(lp) & torch.isfinite(grad.norm(dim=1))
+                self._theta[sl][ok] = cand[ok]
+                todo &= ~ok
+            if bool(todo.any()):
+                raise RuntimeError("failed to initialize")
 
     # ------------------------------------------------------------------ direction law (klhr.py:143-153)
     def _refresh_direction(self):
@@ -145,9 +161,15 @@ class KLHR(MCMCBase):
             adapting = nxt is not None
             steps = n - done
             closes = False
+            snap = False
             if adapting:
-                steps = min(steps, nxt - self._draw, self._pca_stride)
+                # ensemble snapshots sit at ABSOLUTE draw indices (window start + k * stride), so that a run split
+                # by sample() calls or a checkpoint takes them where the uninterrupted run does
+                start, stride = self._window_start(nxt), self._stride_now(nxt)
+                nxt_snap = start + ((self._draw - start) // stride + 1) * stride
+                steps = min(steps, nxt - self._draw, nxt_snap - self._draw)
                 closes = self._draw + steps == nxt
+                snap = self._draw + steps == nxt_snap
             kw = {}
             if adapting and self._moments_every_draw:
                 mom = self._onlinemoments
@@ -156,12 +178,9 @@ class KLHR(MCMCBase):
                 kw.update(shift=stat_shift, chain_s1=chain_s1, chain_s2=chain_s2)
             self._launch(steps, draws=draws, thin=thin, thin_offset=done, **kw)
             if adapting and self._overrelaxed and self._adapt_K:
-                # pooled Smoother signal (klhr.py:219-221): +1 for a chain that moved, -1 otherwise
-                acc_now = float(self._accept_count.double().mean())
-                frac = (acc_now - self._acc_seen) / steps
-                self._acc_seen = acc_now
-                for _ in range(steps - (1 if closes else 0)):
-                    self._smoothK.update(2.0 * frac - 1.0)
+                # Smoother signal (klhr.py:219-221: +1 for a chain that moved, -1 otherwise), pooled over ALL ranks:
+                # the accept counts stay on the device until the closure, where they are summed with the moments
+                self._smooth_log.append((self._accept_count.sum(dtype=torch.float64), steps, steps - (1 if closes else 0)))
             self._draw += steps
             done += steps
             if adapting:
@@ -169,8 +188,22 @@ class KLHR(MCMCBase):
                     self._onlinemoments.add_sums(self.chains * (steps - (1 if closes else 0)))
                 if closes:
                     self._close_window()
-                else:
+                elif snap:
                     self._snapshot_update()
+
+    def _window_start(self, closure):
+        prev = 0
+        for c in self._windowedadaptation.closures:
+            if c >= closure:
+                break
+            prev = c
+        return prev
+
+    def _stride_now(self, closure):
+        if self._pca_stride is not None:
+            return self._pca_stride
+        length = max(1, closure - self._window_start(closure))
+        return max(1, min(length // 4, (self.chains * length) // 2048))
 
     def _launch(self, steps, **kw):
         """``steps`` draws for every chain in one launch (subclasses swap the transition kernel)."""
@@ -180,14 +213,13 @@ class KLHR(MCMCBase):
 
     def _snapshot_update(self):
         """Pooled analogue of klhr.py:216-219 on the current ensemble: PCA second moments of
-        (theta - _mean) and, for ``scale_dir_cov``, gradient moments."""
+        (theta - _mean) and, for ``scale_dir_cov``, gradient moments.  The sums of every slice of 1024 chains go to
+        its own scratch plane; the planes are folded at the closure (bit-reproducible, sharding-invariant)."""
         pca, mom = self._onlinepca, self._onlinemoments
-        if self._outer_scratch is None:       # fixed-order reduction: seeded runs are bit-reproducible
+        if self._outer_scratch is None:
             self._outer_scratch = engine.outer_scratch(self._theta)
-        if self._moments_every_draw:
-            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, scratch=self._outer_scratch)
-        else:       # first moments ride along; second moments are the diagonal of the outer-product sum
-            engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, mom.s1, scratch=self._outer_scratch)
+        engine.outer_accumulate(self._theta, self._shift_dev, pca.outer, mom.s1, scratch=self._outer_scratch)
+        if not self._moments_every_draw:        # first moments ride along; second moments are the diagonal of the outer-product sum
             mom.N += self.chains
         pca.add_sums(self.chains)
         if self._scale_dir_cov:
@@ -197,9 +229,15 @@ class KLHR(MCMCBase):
     def _close_window(self):
         """klhr.py:202-214 with pooled sums; identical result on every rank."""
         mom, gmom, pca = self._onlinemoments, self._onlinemoments_density, self._onlinepca
+        if self._outer_scratch is not None:
+            s1_planes = torch.zeros_like(mom.s1) if self._moments_every_draw else mom.s1
+            engine.outer_reduce(self._outer_scratch, pca.outer, s1_planes, self.chains, self.D)
         if not self._moments_every_draw:
             mom.s2.copy_(torch.diagonal(pca.outer))
-        allreduce_adaptation([mom, gmom], pca, group=self._group)
+        extra = []
+        if self._smooth_log:
+            extra = [torch.stack([t for t, _, _ in self._smooth_log])]
+        allreduce_adaptation([mom, gmom], pca, group=self._group, extra=extra)
         self._mean = mom.mean().cpu().numpy()
         self._cov = mom.var().cpu().numpy()
         if self._scale_dir_cov:
@@ -212,8 +250,19 @@ class KLHR(MCMCBase):
         gmom.reset()
         pca.reset()
         if self._overrelaxed and self._adapt_K:                    # klhr.py:212-214
+            world = 1
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                world = torch.distributed.get_world_size(self._group)
+            if self._smooth_log:
+                tot = extra[0].cpu().numpy() / (self.chains * world)      # mean accepted draws per chain, all ranks
+                for (_, steps, n_upd), acc_now in zip(self._smooth_log, tot):
+                    frac = (acc_now - self._acc_seen) / steps
+                    self._acc_seen = acc_now
+                    for _ in range(n_upd):
+                        self._smoothK.update(2.0 * frac - 1.0)
             self.K = int(np.clip(self._smoothK.optimum(), 1, 50))
             self._fit.overrelax_K = self.K
+        self._smooth_log = []
         self._smoothK.reset()
         self._refresh_direction()
 
@@ -341,7 +390,9 @@ class KLHR(MCMCBase):
             "eigvals": np.array(self._eigvals),
             "moments": [(m.N, m.s1.cpu().clone(), m.s2.cpu().clone(), m.shift.cpu().clone()) for m in (mom, gmom)],
             "pca": (pca.n, pca.outer.cpu().clone()),
+            "planes": None if self._outer_scratch is None else self._outer_scratch.cpu().clone(),
             "smoothK": (self._smoothK._x, self._smoothK._count),
+            "smooth_log": [(float(t), a, b) for t, a, b in self._smooth_log],
         }
 
     def load_state_dict(self, sd):
@@ -366,6 +417,8 @@ class KLHR(MCMCBase):
         self._onlinepca.outer.copy_(sd["pca"][1].to(dev))
         self._onlinepca._eig = None
         self._smoothK._x, self._smoothK._count = sd["smoothK"]
+        self._smooth_log = [(torch.tensor(t, dtype=torch.float64, device=dev), a, b) for t, a, b in sd.get("smooth_log", [])]
+        self._outer_scratch = None if sd.get("planes") is None else sd["planes"].to(dev)
         self._shift_dev = torch.as_tensor(self._mean, dtype=self.dtype, device=dev).contiguous()
         self._refresh_direction()
 

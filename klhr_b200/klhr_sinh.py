@@ -22,7 +22,7 @@ class KLHRSINH(KLHR):
                  windowsize=50, windowscale=2, tol=1e-10, grad_clip=1e15, scale_clip=300,
                  scale_dir_cov=False, overrelaxed=True, eigen_method_one=False, max_init_tries=100, *,
                  chains=1, dtype=torch.float64, device=None, process_group=None, chain_offset=None,
-                 pca_stride=10, moments_every_draw=False, fit_budget=None):
+                 pca_stride=None, moments_every_draw=False, fit_budget=None):
         if dtype != torch.float64:
             raise TypeError("the sinh-arcsinh family needs float64 (sinh/cosh of up to +-300, "
                             "klhr_sinh.py:100-110)")
@@ -37,3 +37,7 @@ class KLHRSINH(KLHR):
 
     def _clip_J(self, J):
         return J                                # klhr_sinh.py:37 does not clip
+
+    def _kl_grad_clip(self):
+        """klhr_sinh.py:158-161: ``KL`` clips every component of the model gradient at ``scale_clip`` (sic)."""
+        return float(self._scale_clip)

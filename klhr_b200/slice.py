@@ -28,7 +28,7 @@ class Slice(KLHR):
     def __init__(self, bsmodel, theta=None, seed=None, w=1, m=np.inf, lower=-np.inf, upper=np.inf, J=2, l=4,
                  initscale=0.1, warmup=1_000, windowsize=50, windowscale=2, tol=1e-12, scale_dir_cov=False,
                  overrelaxed=False, eigen_method_one=True, max_init_tries=100, *, chains=1, dtype=torch.float64,
-                 device=None, process_group=None, chain_offset=None, pca_stride=10, shrink_trace=24):
+                 device=None, process_group=None, chain_offset=None, pca_stride=None, shrink_trace=24):
         if not np.isinf(m):
             raise NotImplementedError("Slice: only m = inf (unlimited stepping out) is supported; the reference's "
                                       "finite-m branch cannot run (slice.py:108,124)")

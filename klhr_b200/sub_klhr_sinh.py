@@ -15,6 +15,10 @@ class SUBKLHRSINH(KLHRSINH):
         super().__init__(bsmodel, *args, **kwargs)
         self._fit.fix_d = True
 
+    def _kl_grad_clip(self):
+        """sub_klhr_sinh.py:152-154: this variant clips at ``grad_clip`` (default 1e15: inactive)."""
+        return float(self._grad_clip)
+
     def fit(self, rho, z_init=None):
         eta = super().fit(rho, z_init=z_init)
         return eta[..., [0, 1, 3]]

@@ -51,23 +51,36 @@ class FitConfig:
     step_cap: float = 2.0            # inf-norm cap of a stage-2 step in scaled coordinates
     c1: float = 1e-4                 # Armijo constant (SciPy's c1, _optimize.py:1156)
     basin: float = 1e-3              # below this scaled-gradient norm take the full Newton step
+    grad_clip: float = 0.0           # sinh family: elementwise clip of the model gradient inside KL
+                                     # (klhr_sinh.py:158-161 clips at scale_clip, sub_klhr_sinh.py:152-154 at grad_clip);
+                                     # applied for dim <= CLIP_MAX_D like the kernels; 0 = off
     eps: float = 2.220446049250313e-16
 
     @staticmethod
     def for_family(family, **kw):
         if family == "sinh":
             base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32)
+            # KLHRSINH clips the model gradient at scale_clip (klhr_sinh.py:158-161); SUBKLHRSINH at grad_clip = 1e15
+            base["grad_clip"] = 1e15 if kw.get("fix_d") else kw.get("scale_clip", 300.0)
         else:
             base = dict(family="gauss")
         base.update(kw)
         return FitConfig(**base)
 
 
+CLIP_MAX_D = 16                      # csrc/klhr_fit.cuh:kClipMaxD
+
+
 # ------------------------------------------------------------------ line restriction
-def line_eval(model, theta, rho, y):
+def line_eval(model, theta, rho, y, grad_clip=0.0):
     """(l(y) - l(0), l'(y), l''(y)) along theta + y rho.  y: (B,) or (B, M).
     Non-finite anywhere -> (-inf, 0, 0), the batched form of reference
-    ``bsmodel.py:15-30`` (failures become -inf / zero gradient)."""
+    ``bsmodel.py:15-30`` (failures become -inf / zero gradient).
+
+    ``grad_clip`` > 0: l' is the projection of the ELEMENTWISE CLIPPED gradient, sum_i clip(g_i, +-c) rho_i, as in
+    ``KLHRSINH.KL`` (``klhr_sinh.py:158-161,171-173``), wherever a component is actually clipped; evaluations on
+    which nothing is clipped keep the plain l'.  l'' is always that of the unclipped density (the Newton matrix of
+    the fixed-iteration optimiser: same fixed points)."""
     y = np.asarray(y, dtype=np.float64)
     flat = y.ndim == 1
     yy = y[:, None] if flat else y
@@ -79,7 +92,11 @@ def line_eval(model, theta, rho, y):
         l = lp - l0[:, None]
         l1 = np.sum(g * rb, axis=-1)
         l2 = model.dir2(pts, rb)
-    bad = ~(np.isfinite(l) & np.isfinite(l1) & np.isfinite(l2))
+        bad = ~(np.isfinite(l) & np.isfinite(l1) & np.isfinite(l2))        # judged on the unclipped evaluation
+        if grad_clip and grad_clip > 0 and theta.shape[-1] <= CLIP_MAX_D:
+            gc = np.clip(g, -grad_clip, grad_clip)
+            hit = np.any(gc != g, axis=-1)
+            l1 = np.where(hit, np.sum(gc * rb, axis=-1), l1)
     l = np.where(bad, -np.inf, l)
     l1 = np.where(bad, 0.0, l1)
     l2 = np.where(bad, 0.0, l2)
@@ -198,8 +215,8 @@ def _kl_sinh(model, theta, rho, eta, x, w, cfg):
     ``klhr_sinh.py:163-176`` in coordinates (m/s, log s, log d, e).  First derivatives are
     the reference's ``_grad_T`` / ``_grad_log_abs_jac`` (:116-124, :146-156); second
     derivatives are those expressions differentiated once more.  The elementwise clip of
-    the model gradient (:158-161) is NOT applied (it cannot be expressed on the line
-    restriction; DESIGN.md "Deviations")."""
+    the model gradient (:158-161) enters through ``line_eval(..., grad_clip)``: l' is the projection
+    of the clipped gradient, l'' stays that of the unclipped density."""
     m, s, d, e = _sinh_unpack(eta, cfg)
     B = len(m)
     c = cfg.scale_clip
@@ -212,7 +229,7 @@ def _kl_sinh(model, theta, rho, eta, x, w, cfg):
         sech2 = 1.0 - th * th
         sN = s[:, None]
         T = m[:, None] + sN * sh
-        l, l1, l2 = line_eval(model, theta, rho, T)
+        l, l1, l2 = line_eval(model, theta, rho, T, grad_clip=cfg.grad_clip)
         logJ = (eta[:, 2] - eta[:, 1])[:, None] - np.log(ch)
         f = np.sum(w * (logJ - l), axis=1)
         # first derivatives (unscaled): order (m, sigma, delta, e)

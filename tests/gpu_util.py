@@ -21,12 +21,13 @@ def fit_pair(family, dtype=torch.float64, **kw):
         kw = dict(kw, fix_d=True)
     if family == "sinh":
         base = dict(family="sinh", tol=1e-10, scale_clip=300.0, n2=48, kmax=32)
+        base["grad_clip"] = 1e15 if kw.get("fix_d") else kw.get("scale_clip", 300.0)   # klhr_sinh.py:158-161 / sub_klhr_sinh.py:152-154
     else:
         base = dict(family="gauss")
     base.update(kw)
     k = kb.FitConfig(**base).for_dtype(dtype)
     o = batched.FitConfig(**{f: getattr(k, f) for f in
-                             ("family", "N", "initscale", "tol", "scale_clip", "n1", "n2", "nb", "kmax", "fix_d", "gtol1",
+                             ("family", "N", "initscale", "tol", "scale_clip", "n1", "n2", "nb", "kmax", "fix_d", "grad_clip", "gtol1",
                               "gtol2", "step_cap", "c1", "basin")})
     if dtype == torch.float32:
         o.eps = float(np.finfo(np.float32).eps)

@@ -23,9 +23,12 @@ def _earnings_data(n=300):
 CASES = [("earnings", None, "gauss"), ("earnings", None, "sinh"), ("funnel", {"D": 4}, "gauss"),
          ("funnel", {"D": 4}, "sinh"), ("rosenbrock", {"D": 3}, "sinh"), ("ill-normal", {"D": 40}, "gauss"),
          ("corr-normal", {"N": 30, "rho": 0.9}, "sinh"), ("arK", "ark", "gauss")]
+# larger states: the elementwise gradient clip of KLHRSINH.KL (klhr_sinh.py:158-161) is ACTIVE on part of the nodes
+CLIPPED = [("funnel", {"D": 4}, 4.0), ("funnel", {"D": 1}, 5.0), ("funnel", {"D": 10}, 3.0), ("arK", "ark", 1.0),
+           ("earnings", None, 2.0), ("rosenbrock", {"D": 3}, 3.0), ("normal", {"D": 5}, 400.0), ("ar1", {"N": 8}, 60.0)]
 
 
-def _setup(model_name, data, family, B):
+def _setup(model_name, data, family, B, scale=0.3):
     if data is None:
         data = _earnings_data()
     if data == "ark":
@@ -35,7 +38,7 @@ def _setup(model_name, data, family, B):
     om = OracleModel(stan_file=f"stan/{model_name}.stan", data=data)
     D = model.dim()
     rng = np.random.default_rng(7)
-    theta = rng.normal(size=(B, D)) * 0.3
+    theta = rng.normal(size=(B, D)) * scale
     rho = rng.normal(size=(B, D))
     rho /= np.linalg.norm(rho, axis=1, keepdims=True)
     n = 2 if family == "gauss" else 4
@@ -53,19 +56,18 @@ def test_kl_matches_port_of_reference_and_finite_differences(model_name, data, f
     f, g, H = f.cpu().numpy(), g.cpu().numpy(), H.cpu().numpy()
     x, w = gauss_hermite_probabilists(8)
     line = (GaussLine(x, w, 1e-12, 600.0) if family == "gauss" else SinhLine(x, w, 1e-10, 300.0))
-    if family == "sinh":
-        # documented deviation: the reference clips the MODEL gradient elementwise to
-        # +-scale_clip before projecting on rho (klhr_sinh.py:158-161); the line restriction cannot express
-        # that, so the comparison is with the port's KL on the unclipped gradient (identical whenever no
-        # gradient component exceeds 300)
-        line.model_grad = lambda mdl, th: mdl.log_density_gradient(th)
     for c in range(B):
         fr, gr = line.kl(eta[c], theta[c], rho[c], om)
         scale = max(1.0, abs(fr))
         assert abs(f[c] - fr) <= 1e-10 * scale, (c, f[c], fr)
         assert np.allclose(g[c], gr, rtol=1e-9, atol=1e-9 * scale), (c, g[c], gr)
     # the reference's self-test: analytic gradient vs central differences of the objective (np.allclose
-    # defaults of klhr.py:259), here with the device objective itself; the Hessian against differences of g
+    # defaults of klhr.py:259), here with the device objective itself; the Hessian against differences of g.
+    # With the elementwise clip active the reference's "gradient" is not the gradient of its objective
+    # (klhr_sinh.py:158-161 clips only the gradient), so the derivative identities are checked with the clip off.
+    import dataclasses
+    kfit = dataclasses.replace(kfit, grad_clip=0.0)
+    f, g, H = (t.cpu().numpy() for t in kb.kl_eval(model, kfit, up(theta), up(rho), up(eta), hessian=True))
     h = 1e-5
     n = eta.shape[1]
     for k in range(n):
@@ -78,6 +80,40 @@ def test_kl_matches_port_of_reference_and_finite_differences(model_name, data, f
         assert np.allclose(num, g[:, k], rtol=1e-5, atol=1e-6 * (1 + np.abs(f))), (k, num[:4], g[:4, k])
         numH = ((gp - gm) / (2 * h)).cpu().numpy()
         assert np.allclose(numH, H[:, :, k], rtol=2e-5, atol=1e-5 * (1 + np.abs(f))[:, None]), k
+
+
+@pytest.mark.parametrize("model_name,data,scale", CLIPPED)
+def test_kl_with_active_gradient_clip_matches_port_of_reference(model_name, data, scale):
+    """KLHRSINH.KL clips every component of the model gradient at scale_clip = 300 before projecting it on rho
+    (klhr_sinh.py:158-161,171-173).  On states where that clip is active the device objective and "gradient" must
+    still be those of the bit-exact port (which applies np.clip exactly like the reference)."""
+    B = 64
+    model, om, kfit, theta, rho, eta = _setup(model_name, data, "sinh", B, scale=scale)
+    assert kfit.grad_clip == 300.0
+    f, g = kb.kl_eval(model, kfit, up(theta), up(rho), up(eta))
+    torch.cuda.synchronize()
+    f, g = f.cpu().numpy(), g.cpu().numpy()
+    x, w = gauss_hermite_probabilists(8)
+    line = SinhLine(x, w, 1e-10, 300.0)
+    hits = [0, 0]
+    inner = line.model_grad
+
+    def counting(mdl, th):
+        lp, gr = mdl.log_density_gradient(th)
+        hits[0] += int(np.any(np.abs(gr) > 300.0))
+        hits[1] += 1
+        return inner(mdl, th)
+    line.model_grad = counting
+    n_ok = 0
+    for c in range(B):
+        fr, gr = line.kl(eta[c], theta[c], rho[c], om)
+        if not (np.isfinite(fr) and np.all(np.isfinite(gr))):
+            continue                      # overflow inside the port's own arithmetic: nothing to compare
+        n_ok += 1
+        scale_f = max(1.0, abs(fr))
+        assert abs(f[c] - fr) <= 1e-9 * scale_f, (c, f[c], fr)
+        assert np.allclose(g[c], gr, rtol=1e-9, atol=1e-9 * max(scale_f, np.abs(gr).max())), (c, g[c], gr)
+    assert n_ok >= B // 2 and hits[0] >= 0.02 * hits[1], (n_ok, hits)        # the clip really was exercised
 
 
 def test_sampler_KL_method_has_the_reference_surface():
@@ -98,5 +134,7 @@ def test_sampler_KL_method_has_the_reference_surface():
     assert g3.shape == (16, 3)
     # d = 1 frozen: the objective of the 4-parameter family at log d = 0, where d = exp(0) + tol = 1 + 1e-10
     sub2 = kb.KLHRSINH(model, seed=1, chains=16, warmup=0)
+    assert sub2._fit.grad_clip == 300.0 and sub._fit.grad_clip == 1e15      # klhr_sinh.py:158-161 vs sub_klhr_sinh.py:152-154
+    sub2._fit.grad_clip = sub._fit.grad_clip
     f4, g4 = sub2.KL(np.array([eta3[0], eta3[1], 0.0, eta3[2]]), rho)
     assert torch.allclose(f3, f4, rtol=1e-8, atol=1e-8) and torch.allclose(g3, g4[:, [0, 1, 3]], rtol=1e-7, atol=1e-6)

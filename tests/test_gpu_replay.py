@@ -79,7 +79,7 @@ def test_against_reference_tape_directly(name):
     t, gpu, ref, _ = _run(name, torch.float64)
     s = np.exp(t["eta"][:, 1])
     assert (np.abs(gpu["eta"][:, 0] - t["eta"][:, 0]) / s).max() <= 1e-5
-    assert np.abs(gpu["eta"][:, 1] - t["eta"][:, 1]).max() <= 1e-9 if "tight" in name else 1e-5
+    assert np.abs(gpu["eta"][:, 1] - t["eta"][:, 1]).max() <= (1e-9 if "tight" in name else 1e-5)
     assert np.array_equal(gpu["accept"], t["accept"])
     assert np.allclose(gpu["theta"][:-1], t["theta0"][1:], atol=1e-4)
 

@@ -65,7 +65,9 @@ def test_funnel_default_gtol_tape(tapes):
 def test_sinh_family_bulk_agreement(tapes, name):
     t, out, em, es = _run(tapes, name)
     good = (em <= 1e-5) & (es <= 1e-5)
-    assert good.mean() >= 0.93
+    # the rest sit in another local optimum of the 4-parameter KL surface (tools/clip_agreement.py: 3.8 % / 1.2 % of
+    # the fits, ours with the lower KL in a third of them); the elementwise gradient clip is applied on both sides
+    assert good.mean() >= 0.955
     assert np.median(em) <= 1e-8 and np.median(es) <= 1e-8
     assert np.array_equal(out["accept"][good], t["accept"][good])
 
