@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip configs c3..c5)")
+    ap.add_argument("--profile-region", default="", choices=["", "c2", "c3", "c4", "c5"],
+                    help="cudaProfilerStart/Stop around the first timed launch of that config (ncu --profile-from-start off)")
     ap.add_argument("--ref-draws-per-step", type=int, default=400)
     ap.add_argument("--ref-procs", type=int, default=0, help="0 = all host cores")
     return ap.parse_args()
@@ -299,7 +301,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         return max_over_ranks(time.perf_counter() - t0)
 
-    def timed_steps(sampler, draws, k, w, do_flush):
+    def timed_steps(sampler, draws, k, w, do_flush, tag=""):
         """k launches of `draws` draws, each bracketed by CUDA events on the launching stream; max over ranks of
         the summed device time.  Returns (total_ms, wall window)."""
         for _ in range(w):
@@ -312,9 +314,16 @@ def run_b200(args):
         for i in range(k):
             if do_flush:
                 flush.zero_()                      # L2 flush between timed iterations
+            prof_this = bool(tag) and args.profile_region == tag and i == 0
+            if prof_this:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
             evs[i][0].record()
             sampler.run(draws)                     # ONE klhr_run launch: all chains x `draws` draws
             evs[i][1].record()
+            if prof_this:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
         torch.cuda.synchronize()
         barrier()
         w1 = time.time()
@@ -348,7 +357,7 @@ def run_b200(args):
     sampler = kb.KLHR(model, seed=SEED, chains=B, warmup=args.adapt_warmup, windowsize=50, windowscale=2,
                       dtype=dtype, device=dev)
     adapt_s = adapt_phase(sampler, args.adapt_warmup)     # windows close at 50,150,350,1000 (+ all-reduce)
-    total_ms, (wall0, wall1) = timed_steps(sampler, S, K, W, True)
+    total_ms, (wall0, wall1) = timed_steps(sampler, S, K, W, True, "c2")
     value = world * B * S * K / (total_ms * 1e-3)
     info = kb.launch_info(model, sampler._fit, dtype=dtype, free_running=True, accumulate=False, device=dev)
 
@@ -472,7 +481,7 @@ def run_b200(args):
             smp = make_sampler()
             a_s = adapt_phase(smp, 1000)
             a_draws = world * smp.chains * 1000
-            t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, 2, False)
+            t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, 2, False, tag)
             val = world * smp.chains * draws * Kc / (t_ms * 1e-3)
             ev0 = int(smp._evals_total.item())
             smp.run(draws)
