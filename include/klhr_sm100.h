@@ -35,7 +35,9 @@ enum {
     KLHR_MODEL_NORMAL = 0,      /* stan/normal.stan       */
     KLHR_MODEL_ILL_NORMAL = 1,  /* stan/ill-normal.stan   data0 = inv_s2[D]                       */
     KLHR_MODEL_FUNNEL = 2,      /* stan/funnel.stan       i0 = D (number of alpha); dim = D + 1   */
-    KLHR_MODEL_CORR_NORMAL = 3, /* stan/corr-normal.stan  data0 = dense precision P[D*D]          */
+    KLHR_MODEL_CORR_NORMAL = 3, /* stan/corr-normal.stan  data0 = dense precision P[D*D]; data1 (optional, fp64) =
+                                   lower Cholesky factor L[D*D] of P, row-major, zeros above the diagonal:
+                                   enables the triangular tensor-core kernel for D = 128 / 256             */
     KLHR_MODEL_AR1 = 4,         /* stan/ar1.stan          s0 = alpha, s1 = 1/beta^2               */
     KLHR_MODEL_ARK = 5,         /* stan/arK.stan          i0 = K, i1 = T-K, data0 = [G|c|yy]      */
     KLHR_MODEL_ROSENBROCK = 6,  /* stan/rosenbrock.stan   i0 = D; dim = 2 D                       */
@@ -51,7 +53,7 @@ typedef struct klhr_model {
     double s0, s1;       /* model scalars, see enum                    */
     const void* data0;   /* device buffer, see enum: `dtype` reals, except the sufficient statistics
                             of arK and earnings which are ALWAYS fp64   */
-    const void* data1;   /* reserved                                   */
+    const void* data1;   /* second device buffer, see enum (NULL if unused) */
 } klhr_model_t;
 
 #define KLHR_MAX_NODES 32

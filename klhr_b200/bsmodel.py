@@ -55,7 +55,7 @@ class BSModel:
     # ------------------------------------------------------------------ host-side "transformed data"
     def _prepare_host(self):
         d, n = self.data, self.name
-        h = dict(i0=0, i1=0, s0=0.0, s1=0.0, data0=None)
+        h = dict(i0=0, i1=0, s0=0.0, s1=0.0, data0=None, data1=None)
         if n == "normal":
             h["dim"] = int(d["D"])
         elif n == "ill-normal":                      # stan/ill-normal.stan:4-6
@@ -69,7 +69,9 @@ class BSModel:
             idx = np.arange(N)
             Sigma = rho ** np.abs(idx[:, None] - idx[None, :])
             P = np.linalg.inv(Sigma)
-            h.update(dim=N, data0=(0.5 * (P + P.T)).reshape(-1))
+            P = 0.5 * (P + P.T)
+            # P = L L' (fp64): the dense kernel works with V = L' rho and w = L' theta (csrc/klhr_densek.cuh)
+            h.update(dim=N, data0=P.reshape(-1), data1=np.tril(np.linalg.cholesky(P)).reshape(-1))
         elif n == "ar1":                             # stan/ar1.stan:4-7
             alpha = 0.9
             h.update(dim=int(d["N"]), s0=alpha, s1=1.0 / (1.0 - alpha * alpha))
@@ -111,10 +113,14 @@ class BSModel:
                 # sufficient statistics (arK, earnings) stay fp64 whatever the arithmetic type (klhr_models.cuh)
                 bt = torch.float64 if self.name in ("arK", "earnings") else dtype
                 buf = torch.as_tensor(h["data0"], dtype=torch.float64).to(device=device, dtype=bt).contiguous()
+            buf1 = None
+            if h.get("data1") is not None and dtype == torch.float64:
+                buf1 = torch.as_tensor(h["data1"], dtype=torch.float64).to(device=device).contiguous()
             desc = _lib.ModelDesc(id=_lib.MODEL_IDS[self.name], dim=h["dim"], i0=h["i0"], i1=h["i1"],
                                   s0=h["s0"], s1=h["s1"],
-                                  data0=buf.data_ptr() if buf is not None else None, data1=None)
-            self._cache[key] = (desc, buf)
+                                  data0=buf.data_ptr() if buf is not None else None,
+                                  data1=buf1.data_ptr() if buf1 is not None else None)
+            self._cache[key] = (desc, buf, buf1)
         return self._cache[key][0]
 
     # ------------------------------------------------------------------ evaluation

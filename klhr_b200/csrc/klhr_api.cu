@@ -8,6 +8,7 @@
 
 #include "klhr_chain.cuh"
 #include "klhr_lane.cuh"
+#include "klhr_densek.cuh"
 #include "klhr_mh.cuh"
 #include "klhr_slice.cuh"
 
@@ -133,6 +134,7 @@ static int dispatch_chain(const StepArgs& a, int dtype, int family, bool replay,
 static int dispatch_step(const StepArgs& a, int dtype, int family, bool replay, bool accum, cudaStream_t st,
                          LaunchInfo* info, int flags) {
     if (lane_applies(a, dtype, family, replay, accum, flags)) return launch_lane(a, st, info);
+    if (densek_applies(a, dtype, family, replay, accum, flags)) return launch_densek(a, replay, st, info);
     if (tile_applies(a, family, accum, flags)) return launch_tile(a, dtype, replay, st, info);
     if (chain_applies(a, dtype, replay, accum, flags)) return dispatch_chain(a, dtype, family, replay, st, info);
     switch (a.mp.id) {

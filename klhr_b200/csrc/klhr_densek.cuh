@@ -1,0 +1,391 @@
+// klhr_b200 -- the DENSE kernel: stan/corr-normal.stan (dense precision), Gaussian line family, fp64,
+// D = 128 or 256; chain state resident in shared memory for the whole launch, 32 chains per CTA.
+//
+// The line restriction of a Gaussian target needs A = rho' P rho and Bq = -theta' P rho per chain and draw
+// (reference klhr.py:106-124 evaluates lp through the full D-vector at every node instead).  With the Cholesky
+// factor P = L L' (host, fp64, BSModel) both are inner products of TRIANGULAR images:
+//     V = L' rho,   A = V.V,   Bq = -(L' theta).V
+// and w = L' theta follows the chain by the same V: theta' = theta + zp rho  =>  w' = w + zp V.  So one
+// triangular product per draw (D^2 flops per chain instead of the 2 D^2 of P rho) gives everything, and w never
+// has to be recomputed inside a launch (it is rebuilt from theta by the same product when a launch starts).
+//
+// Shape.  A CTA of 8 warps owns 32 chains.  X (the un-normalised directions, 32 x D) and theta live in shared
+// memory; V = X L runs on mma.sync.m8n8k4.f64: warp w owns the column tiles {w, 15-w, 16+w, 31-w} of L (equal
+// DMMA counts for every warp although tile n only needs k >= 8 n), its accumulator fragments ARE V for those
+// columns, and the matching fragments of w stay in registers for the whole launch -- V and w are never written
+// to memory.  The B fragments of L stream L2 -> shared memory through a per-warp cp.async ring 8 k-steps deep
+// (each lane copies exactly the 8 bytes it will consume: no barrier, no bank conflict), so the L2 latency sits
+// behind 8 x 16 DMMAs.  The fit of a quadratic target is closed form (quad_fit_closed, klhr_lane.cuh); chains
+// whose premises fail take the generic iteration of klhr_fit.cuh, so every path returns the same iterates.
+// Variate streams are the same function of (seed, chain, draw, element) as in every other kernel.
+#pragma once
+#include "klhr_lane.cuh"
+
+namespace klhr {
+
+constexpr int kDkChains = 32;
+constexpr int kDkThreads = 256;
+constexpr int kDkWarps = kDkThreads / 32;
+constexpr int kDkDepth = 8;                       // k-steps of L in flight per warp
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// column tile q (0..NT-1) of warp w: ascending in q, and sum_q tile = const for every warp
+__device__ __forceinline__ int dk_tile(int q, int w) { return (q & 1) ? 8 * (q - 1) + 15 - w : 8 * q + w; }
+
+// acc[m][q][e] = sum_k rows[8 m + r8][k] * L[k][8 tile_q + 2 k4 + e]   (k >= 8 tile_q: L is lower triangular)
+// rows: [32][S] in shared memory; ring: this warp's [kDkDepth][NT][32] staging doubles.
+template <int NT>
+__device__ __forceinline__ void dk_tri_product(const double* __restrict__ rows, int S, const double* __restrict__ Lm, int D,
+                                               double* ring, int warp, int lane, double (&acc)[4][NT][2]) {
+    const int r8 = lane >> 2, k4 = lane & 3;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int q = 0; q < NT; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
+    int kst[NT];
+    const double* gq[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+        kst[q] = 8 * dk_tile(q, warp);
+        gq[q] = Lm + (size_t)k4 * D + 8 * dk_tile(q, warp) + r8;       // + k0 * D per k-step
+    }
+    const int kb = kst[0];
+    const int n_steps = (D - kb) >> 2;
+    double* my_ring = ring + lane;
+    auto issue = [&](int i) {                          // k-step i (k0 = kb + 4 i) into slot i % depth
+        const int k0 = kb + 4 * i;
+        if (i < n_steps) {
+            double* dst = my_ring + (size_t)(i % kDkDepth) * NT * 32;
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+                if (k0 >= kst[q]) cp_async8(dst + q * 32, gq[q] + (size_t)k0 * D);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kDkDepth - 1; ++i) issue(i);
+    const double* ar = rows + (size_t)r8 * S + k4;
+    auto segment = [&](auto na_tag, int i_begin, int i_end) {
+        constexpr int NA = decltype(na_tag)::value;
+#pragma unroll 2
+        for (int i = i_begin; i < i_end; ++i) {
+            issue(i + kDkDepth - 1);
+            cp_async_wait<kDkDepth - 1>();
+            const int k0 = kb + 4 * i;
+            const double* slot = my_ring + (size_t)(i % kDkDepth) * NT * 32;
+            double av[4], bv[NA];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) av[m] = ar[(size_t)8 * m * S + k0];
+#pragma unroll
+            for (int q = 0; q < NA; ++q) bv[q] = slot[q * 32];
+#pragma unroll
+            for (int q = 0; q < NA; ++q)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], av[m], bv[q]);
+        }
+    };
+    // segment s: tiles 0..s active, k in [kst[s], kst[s+1])
+    if constexpr (NT == 2) {
+        segment(std::integral_constant<int, 1>{}, 0, (kst[1] - kb) >> 2);
+        segment(std::integral_constant<int, 2>{}, (kst[1] - kb) >> 2, n_steps);
+    } else {
+        segment(std::integral_constant<int, 1>{}, 0, (kst[1] - kb) >> 2);
+        segment(std::integral_constant<int, 2>{}, (kst[1] - kb) >> 2, (kst[2] - kb) >> 2);
+        segment(std::integral_constant<int, 3>{}, (kst[2] - kb) >> 2, (kst[3] - kb) >> 2);
+        segment(std::integral_constant<int, 4>{}, (kst[3] - kb) >> 2, n_steps);
+    }
+    cp_async_wait<0>();
+}
+
+template <int NT, bool kReplay, bool kDraws>
+__global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_constant__ StepArgs a) {
+    using R = double;
+    using Model = CorrNormal<R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.mp.D;                              // 64 NT
+    const int S = D + 4;                               // row pitch: = 4 (mod 16) doubles -> conflict-free A fragments
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int o = tid >> 3, j = tid & 7;               // octet o = chain slot, lane j of the octet
+    const unsigned om = oct_mask();
+    const int r8 = lane >> 2, k4 = lane & 3;
+    const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+    const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
+    // shared memory (doubles first): th[32][S] | xs[32][S] | ring[8][depth][NT][32] | red[8][32][2] | s_inv[32] | s_c[32]
+    //   | s_zi[32] | s_zp[32] | s_u[32] | (floats) sd[D] | mean[n_stored][D] | cdf[n_cols]
+    R* th_all = reinterpret_cast<R*>(smem_raw);
+    R* xs_all = th_all + (size_t)kDkChains * S;
+    R* ring_all = xs_all + (size_t)kDkChains * S;
+    R* red = ring_all + (size_t)kDkWarps * kDkDepth * NT * 32;
+    R* s_inv = red + kDkWarps * kDkChains * 2;
+    R* s_c = s_inv + kDkChains;
+    R* s_zi = s_c + kDkChains;
+    R* s_zp = s_zi + kDkChains;
+    R* s_u = s_zp + kDkChains;
+    float* s_sd = reinterpret_cast<float*>(s_u + kDkChains);
+    float* s_mean = s_sd + D;
+    float* s_cdf = s_mean + (size_t)n_stored * D;
+    R* th = th_all + (size_t)o * S;
+    R* xs = xs_all + (size_t)o * S;
+    R* ring = ring_all + (size_t)warp * kDkDepth * NT * 32;
+
+    const long long c = (long long)blockIdx.x * kDkChains + o;      // chain of this octet
+    const bool valid = c < a.B;
+    const long long c_fit = (long long)blockIdx.x * kDkChains + tid; // chain fitted by thread tid < 32
+    R* g_theta = reinterpret_cast<R*>(a.theta);
+    const R* Lm = reinterpret_cast<const R*>(a.mp.p1);
+
+    if constexpr (!kReplay) {
+        const R* g_sd = reinterpret_cast<const R*>(a.dir.sd);
+        const R* g_mean = reinterpret_cast<const R*>(a.dir.mean_cols);
+        for (int i = tid; i < D; i += kDkThreads) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
+        for (int i = tid; i < n_stored * D; i += kDkThreads) s_mean[i] = (float)g_mean[i];
+        for (int i = tid; i < n_cols; i += kDkThreads) s_cdf[i] = n_cols > 1 ? (float)reinterpret_cast<const R*>(a.dir.cdf)[i] : 1.0f;
+    }
+    for (int i = j; i < S; i += kOct) {
+        th[i] = (valid && i < D) ? g_theta[c * D + i] : R(0);
+        xs[i] = R(0);
+    }
+    __syncthreads();
+
+    // w = L' theta for this thread's fragment positions (rows 8 m + r8, columns 8 tile_q + 2 k4 + e)
+    double wf[4][NT][2];
+    dk_tri_product<NT>(th_all, S, Lm, D, ring, warp, lane, wf);
+
+    const R tol = (R)a.fp.tol;
+    const uint32_t k0s = (uint32_t)a.seed, k1s = (uint32_t)(a.seed >> 32);
+    const unsigned long long cid = (unsigned long long)(a.chain_offset + c);
+    const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
+    long long n_acc = 0;
+    unsigned long long n_evals = 0;
+
+    for (int step = 0; step < a.n_steps; ++step) {
+        const long long row = (long long)step * a.B + c;
+        // ---------------------------------------------------------------- A. variates and direction (octet per chain)
+        if (valid) {
+            if constexpr (kReplay) {
+                const R* g_rho = reinterpret_cast<const R*>(a.rho);
+                for (int i = j; i < D; i += kOct) xs[i] = g_rho[c * D + i];
+                if (j == 0) {
+                    s_inv[o] = R(1);
+                    s_zi[o] = reinterpret_cast<const R*>(a.z_init)[c];
+                    s_zp[o] = reinterpret_cast<const R*>(a.z_prop)[c];
+                    s_u[o] = reinterpret_cast<const R*>(a.u)[c];
+                }
+            } else {
+                const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
+                const uint32_t d0 = (uint32_t)draw, k1d = k1s ^ (uint32_t)(draw >> 32);
+                // scalar variates (slots 0..2, same mapping as chain_scalars): lanes 0..2 expand one slot each
+                R sv0 = 0, sv1 = 0;
+                if (j < 3) {
+                    uint32_t wv[4];
+                    Philox::block(c0, c1, d0, (uint32_t)j, k0s, k1d, wv);
+                    if (j == 0) {
+                        float z0, z1;
+                        box_muller_f32(wv[2], wv[3], z0, z1);
+                        sv0 = (R)u01_32(wv[0]);
+                        sv1 = (R)z0;
+                    } else if (j == 1) {
+                        sv0 = box_muller_f64(u01_53(wv[0], wv[1]), u01_53(wv[2], wv[3]));
+                    } else {
+                        sv0 = u01_53(wv[0], wv[1]);
+                    }
+                }
+                const R u_col = oct_bcast(sv0, 0, om);
+                int jcol = 0;
+                if (n_cols > 1)                            // searchsorted(cdf, u, 'right'), klhr.py:147
+                    while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
+                if (j == 0) s_zi[o] = sv1;
+                if (j == 1) s_zp[o] = sv0;
+                if (j == 2) s_u[o] = sv0;
+                const float* mcol = (n_cols && jcol < n_stored) ? s_mean + (size_t)jcol * D : nullptr;
+                // element i = g0 + j + 32 t + 8 r  <->  Philox slot kSlotDir + j + 8 t + g0 / 4, word r
+                R ss = 0;
+                for (int g0 = 0; g0 < D; g0 += 128) {
+                    uint32_t wv[4][4];
+                    Philox::blockN<4>(c0, c1, d0, kSlotDir + (uint32_t)j + (uint32_t)(g0 / 4), 8u, k0s, k1d, wv);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float z[4];
+                        box_muller_f32(wv[t][0], wv[t][1], z[0], z[1]);
+                        box_muller_f32(wv[t][2], wv[t][3], z[2], z[3]);
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int i = g0 + j + 32 * t + 8 * rr;
+                            const R x = (R)fmaf(s_sd[i], z[rr], mcol ? mcol[i] : 0.0f);
+                            xs[i] = x;
+                            const R xt = x + tol;
+                            ss += xt * xt;
+                        }
+                    }
+                }
+                ss = oct_sum(ss, om);
+                if (j == 0) s_inv[o] = R(1) / r_sqrt(ss);      // rho = x / ||x + tol||  (klhr.py:153)
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- B. V = X L on the FP64 tensor cores
+        double vf[4][NT][2];
+        dk_tri_product<NT>(xs_all, S, Lm, D, ring, warp, lane, vf);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            double pa = 0, pb = 0;
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    pa = fma(vf[m][q][e], vf[m][q][e], pa);
+                    pb = fma(wf[m][q][e], vf[m][q][e], pb);
+                }
+            pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+            pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+            pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+            pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+            if (k4 == 0) {
+                red[(warp * kDkChains + 8 * m + r8) * 2 + 0] = pa;
+                red[(warp * kDkChains + 8 * m + r8) * 2 + 1] = pb;
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- C. fit, proposal, MH (thread per chain)
+        if (tid < kDkChains) {
+            R cmove = 0;
+            if (c_fit < a.B) {
+                double sA = 0, sB = 0;
+#pragma unroll
+                for (int w8 = 0; w8 < kDkWarps; ++w8) {        // fixed order: deterministic
+                    sA += red[(w8 * kDkChains + tid) * 2 + 0];
+                    sB += red[(w8 * kDkChains + tid) * 2 + 1];
+                }
+                const R inv = s_inv[tid];
+                typename Model::Coef cf;
+                cf.A = __dmul_rn(__dmul_rn(sA, inv), inv);
+                cf.Bq = __dmul_rn(-sB, inv);
+                const R z_init = s_zi[tid], z_prop = s_zp[tid], u = s_u[tid];
+                StepOut<R> so;
+                if (!quad_fit_closed(cf.A, cf.Bq, z_init, z_prop, r_log(u), a.fp, a.tr.eta != nullptr, so)) {
+                    OrCtx<R> oc;
+                    oc.K = 0; oc.inject = false; oc.r = 0; oc.v = 1;
+                    fit_and_propose<1, R, Model, 2>(cf, a.fp, 0, 0u, z_init, R(0), R(0), z_prop, u, so, oc);
+                }
+                cmove = so.accept ? __dmul_rn(so.zp, inv) : R(0);
+                n_acc += so.accept ? 1 : 0;
+                n_evals += (unsigned long long)so.evals;
+                const long long trow = (long long)step * a.B + c_fit;
+                if (a.tr.eta) {
+                    R* e = reinterpret_cast<R*>(a.tr.eta) + trow * 2;
+                    e[0] = so.eta[0];
+                    e[1] = so.eta[1];
+                }
+                if (a.tr.zp) reinterpret_cast<R*>(a.tr.zp)[trow] = so.zp;
+                if (a.tr.r) reinterpret_cast<R*>(a.tr.r)[trow] = so.r;
+                if (a.tr.accept) a.tr.accept[trow] = so.accept ? 1 : 0;
+                if (a.tr.evals) a.tr.evals[trow] = so.evals;
+                if (!kReplay && a.tr.z_init) {
+                    reinterpret_cast<R*>(a.tr.z_init)[trow] = z_init;
+                    reinterpret_cast<R*>(a.tr.z_prop)[trow] = z_prop;
+                    reinterpret_cast<R*>(a.tr.u)[trow] = u;
+                }
+            }
+            s_c[tid] = cmove;
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- D. move: theta += c x, w += c V
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const R cm = s_c[8 * m + r8];
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                wf[m][q][0] = fma(cm, vf[m][q][0], wf[m][q][0]);
+                wf[m][q][1] = fma(cm, vf[m][q][1], wf[m][q][1]);
+            }
+        }
+        if (valid) {
+            if (a.tr.rho) {                                    // rho = x / ||x + tol|| (tests)
+                R* g = reinterpret_cast<R*>(a.tr.rho) + row * D;
+                const R inv = s_inv[o];
+                for (int i = j; i < D; i += kOct) g[i] = xs[i] * inv;
+            }
+            const R cm = s_c[o];
+            if (cm != R(0))
+                for (int i = j; i < D; i += kOct) th[i] = fma(cm, xs[i], th[i]);
+            if constexpr (kDraws) {
+                const long long gdraw = a.acc.thin_offset + step + 1;
+                if (gdraw % a.acc.thin == 0) {
+                    R* g = reinterpret_cast<R*>(a.acc.draws) + ((gdraw / a.acc.thin - 1) * a.B + c) * D;
+                    for (int i = j; i < D; i += kOct) g[i] = th[i];
+                }
+            }
+        }
+        // no barrier: phase A of the next draw writes only this octet's own xs row and scalars, which nobody
+        // else reads before the barrier that follows it; s_c / red are rewritten two barriers from here
+    }
+    if (valid)
+        for (int i = j; i < D; i += kOct) g_theta[c * D + i] = th[i];
+    if (tid < kDkChains) {
+        if (c_fit < a.B && a.acc.accept_count) a.acc.accept_count[c_fit] += n_acc;
+        if (a.acc.evals_total) {
+            unsigned long long tot = c_fit < a.B ? n_evals : 0ull;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+            if (tid == 0 && tot) atomicAdd(a.acc.evals_total, tot);
+        }
+    }
+}
+
+__host__ inline size_t densek_smem_bytes(const StepArgs& a, bool replay) {
+    const int D = a.mp.D, S = D + 4, NT = D / 64;
+    const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
+    const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
+    size_t b = (size_t)2 * kDkChains * S * 8;                                  // theta, x
+    b += (size_t)kDkWarps * kDkDepth * NT * 32 * 8;                            // cp.async rings
+    b += (size_t)(kDkWarps * kDkChains * 2 + 5 * kDkChains) * 8;               // red, inv, c, z_init, z_prop, u
+    b += (size_t)(D + (size_t)n_stored * D + ((n_cols + 3) & ~3)) * 4;         // sd, mean columns, cdf
+    return b;
+}
+
+// fp64, Gaussian family, no in-kernel accumulators, standard proposals, Cholesky factor supplied, D = 128 | 256
+__host__ inline bool densek_applies(const StepArgs& a, int dtype, int family, bool replay, bool accum, int flags) {
+    return !(flags & KLHR_FIT_FORCE_OCTET) && dtype == KLHR_F64 && family == KLHR_FAMILY_GAUSS && !accum &&
+           a.fp.or_K == 0 && a.mp.id == KLHR_MODEL_CORR_NORMAL && a.mp.p1 != nullptr &&
+           (a.mp.D == 128 || a.mp.D == 256) && densek_smem_bytes(a, replay) <= (size_t)227 * 1024;
+}
+
+template <int NT>
+int launch_densek_nt(const StepArgs& a, bool replay, cudaStream_t st, LaunchInfo* info) {
+    const size_t smem = densek_smem_bytes(a, replay);
+    const bool draws = !replay && a.acc.draws != nullptr;
+    const void* fn = replay ? (const void*)dense_kernel<NT, true, false>
+                            : (draws ? (const void*)dense_kernel<NT, false, true> : (const void*)dense_kernel<NT, false, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (info) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) return (int)e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kDkThreads, smem);
+        if (e != cudaSuccess) return (int)e;
+        info->threads = kDkThreads;
+        info->smem = (int)smem;
+        info->regs = fa.numRegs;
+        info->ctas_per_sm = nb;
+        return 0;
+    }
+    const long long grid = (a.B + kDkChains - 1) / kDkChains;
+    if (grid <= 0) return 0;
+    void* kargs[] = {(void*)&a};
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kDkThreads), kargs, smem, st);
+    return (int)e;
+}
+
+// defined in klhr_densek.cu
+int launch_densek(const StepArgs& a, bool replay, cudaStream_t st, LaunchInfo* info);
+
+}  // namespace klhr
