@@ -23,10 +23,19 @@
 
 namespace klhr {
 
-constexpr int kDkChains = 32;
+#ifndef KLHR_DENSEK_CHAINS
+#define KLHR_DENSEK_CHAINS 32
+#endif
+// chains per CTA.  Measured on B200 (D = 256, 16 384 chains): 32 chains, one CTA per SM 2.30e8 draws/s; 16 chains, two CTAs
+// per SM (their tensor-core and scalar phases interleave, but every L fragment feeds half as many DMMAs and the
+// k-loop overhead per DMMA doubles) 2.09e8
+constexpr int kDkChains = KLHR_DENSEK_CHAINS;
 constexpr int kDkThreads = 256;
 constexpr int kDkWarps = kDkThreads / 32;
-constexpr int kDkDepth = 8;                       // k-steps of L in flight per warp
+constexpr int kDkDepth = kDkChains == 16 ? 4 : 8;  // k-steps of L in flight per warp (two CTAs per SM need <= 113 KB each)
+constexpr int kDkMT = kDkChains / 8;              // m8 row tiles
+constexpr int kDkLpc = kDkThreads / kDkChains;    // lanes per chain in the vector phases (8 or 16)
+static_assert(kDkChains == 16 || kDkChains == 32, "dense kernel: 16 or 32 chains per CTA");
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -39,105 +48,121 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // column tile q (0..NT-1) of warp w: ascending in q, and sum_q tile = const for every warp
 __device__ __forceinline__ int dk_tile(int q, int w) { return (q & 1) ? 8 * (q - 1) + 15 - w : 8 * q + w; }
 
-// acc[m][q][e] = sum_k rows[8 m + r8][k] * L[k][8 tile_q + 2 k4 + e]   (k >= 8 tile_q: L is lower triangular)
-// rows: [32][S] in shared memory; ring: this warp's [kDkDepth][NT][32] staging doubles.
-template <int NT>
+// acc[m][q][e] (m < MT row tiles) = sum_k rows[8 m + r8][k] * L[k][8 tile_q + 2 k4 + e]   (k >= 8 tile_q: L is lower triangular)
+// rows: [8 MT][S] in shared memory; ring: this warp's [kDkDepth][NT][32] staging doubles.
+template <int MT, int NT>
 __device__ __forceinline__ void dk_tri_product(const double* __restrict__ rows, int S, const double* __restrict__ Lm, int D,
-                                               double* ring, int warp, int lane, double (&acc)[4][NT][2]) {
+                                               double* ring, int warp, int lane, double (&acc)[MT][NT][2]) {
     const int r8 = lane >> 2, k4 = lane & 3;
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int q = 0; q < NT; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-    int kst[NT];
-    const double* gq[NT];
+    int ist[NT];                                       // first k-step (relative to this warp's first tile) of tile q
+    const int kb = 8 * dk_tile(0, warp);
+    const double* gp[NT];                              // B-fragment source of tile q at the NEXT k-step to issue
 #pragma unroll
     for (int q = 0; q < NT; ++q) {
-        kst[q] = 8 * dk_tile(q, warp);
-        gq[q] = Lm + (size_t)k4 * D + 8 * dk_tile(q, warp) + r8;       // + k0 * D per k-step
+        ist[q] = (8 * dk_tile(q, warp) - kb) >> 2;
+        gp[q] = Lm + (size_t)(kb + k4) * D + 8 * dk_tile(q, warp) + r8;
     }
-    const int kb = kst[0];
     const int n_steps = (D - kb) >> 2;
+    const size_t gstride = (size_t)4 * D;
     double* my_ring = ring + lane;
-    auto issue = [&](int i) {                          // k-step i (k0 = kb + 4 i) into slot i % depth
-        const int k0 = kb + 4 * i;
-        if (i < n_steps) {
-            double* dst = my_ring + (size_t)(i % kDkDepth) * NT * 32;
+    int i_issue = 0, slot_w = 0;
+    auto issue = [&]() {                               // k-step i_issue into ring slot i_issue % depth
+        if (i_issue < n_steps) {
+            double* dst = my_ring + slot_w * (NT * 32);
 #pragma unroll
-            for (int q = 0; q < NT; ++q)
-                if (k0 >= kst[q]) cp_async8(dst + q * 32, gq[q] + (size_t)k0 * D);
+            for (int q = 0; q < NT; ++q) {
+                if (i_issue >= ist[q]) cp_async8(dst + q * 32, gp[q]);
+                gp[q] += gstride;
+            }
         }
         cp_async_commit();
+        ++i_issue;
+        slot_w = (slot_w + 1) & (kDkDepth - 1);
     };
 #pragma unroll
-    for (int i = 0; i < kDkDepth - 1; ++i) issue(i);
-    const double* ar = rows + (size_t)r8 * S + k4;
+    for (int i = 0; i < kDkDepth - 1; ++i) issue();
+    const double* ar = rows + (size_t)r8 * S + k4 + kb;
+    const size_t s8 = (size_t)8 * S;
+    int slot_r = 0;
     auto segment = [&](auto na_tag, int i_begin, int i_end) {
         constexpr int NA = decltype(na_tag)::value;
 #pragma unroll 2
         for (int i = i_begin; i < i_end; ++i) {
-            issue(i + kDkDepth - 1);
+            issue();
             cp_async_wait<kDkDepth - 1>();
-            const int k0 = kb + 4 * i;
-            const double* slot = my_ring + (size_t)(i % kDkDepth) * NT * 32;
-            double av[4], bv[NA];
+            const double* slot = my_ring + slot_r * (NT * 32);
+            slot_r = (slot_r + 1) & (kDkDepth - 1);
+            double av[MT], bv[NA];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) av[m] = ar[(size_t)8 * m * S + k0];
+            for (int m = 0; m < MT; ++m) av[m] = ar[m * s8];
+            ar += 4;
 #pragma unroll
             for (int q = 0; q < NA; ++q) bv[q] = slot[q * 32];
 #pragma unroll
             for (int q = 0; q < NA; ++q)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], av[m], bv[q]);
+                for (int m = 0; m < MT; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], av[m], bv[q]);
         }
     };
-    // segment s: tiles 0..s active, k in [kst[s], kst[s+1])
+    // segment s: tiles 0..s active, k-steps [ist[s], ist[s+1])
     if constexpr (NT == 2) {
-        segment(std::integral_constant<int, 1>{}, 0, (kst[1] - kb) >> 2);
-        segment(std::integral_constant<int, 2>{}, (kst[1] - kb) >> 2, n_steps);
+        segment(std::integral_constant<int, 1>{}, 0, ist[1]);
+        segment(std::integral_constant<int, 2>{}, ist[1], n_steps);
     } else {
-        segment(std::integral_constant<int, 1>{}, 0, (kst[1] - kb) >> 2);
-        segment(std::integral_constant<int, 2>{}, (kst[1] - kb) >> 2, (kst[2] - kb) >> 2);
-        segment(std::integral_constant<int, 3>{}, (kst[2] - kb) >> 2, (kst[3] - kb) >> 2);
-        segment(std::integral_constant<int, 4>{}, (kst[3] - kb) >> 2, n_steps);
+        segment(std::integral_constant<int, 1>{}, 0, ist[1]);
+        segment(std::integral_constant<int, 2>{}, ist[1], ist[2]);
+        segment(std::integral_constant<int, 3>{}, ist[2], ist[3]);
+        segment(std::integral_constant<int, 4>{}, ist[3], n_steps);
     }
     cp_async_wait<0>();
 }
 
+// sum over the kDkLpc consecutive lanes that share a chain
+__device__ __forceinline__ double dk_grp_sum(double v) {
+#pragma unroll
+    for (int off = 1; off < kDkLpc; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
 template <int NT, bool kReplay, bool kDraws>
-__global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const __grid_constant__ StepArgs a) {
     using R = double;
     using Model = CorrNormal<R>;
+    constexpr int CH = kDkChains, MT = kDkMT, LPC = kDkLpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.mp.D;                              // 64 NT
     const int S = D + 4;                               // row pitch: = 4 (mod 16) doubles -> conflict-free A fragments
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int o = tid >> 3, j = tid & 7;               // octet o = chain slot, lane j of the octet
-    const unsigned om = oct_mask();
+    const int o = tid / LPC, j = tid % LPC;            // chain slot o, lane j of the chain's group
     const int r8 = lane >> 2, k4 = lane & 3;
     const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
-    // shared memory (doubles first): th[32][S] | xs[32][S] | ring[8][depth][NT][32] | red[8][32][2] | s_inv[32] | s_c[32]
-    //   | s_zi[32] | s_zp[32] | s_u[32] | (floats) sd[D] | mean[n_stored][D] | cdf[n_cols]
+    // shared memory (doubles first): th[CH][S] | xs[CH][S] | ring[8][depth][NT][32] | red[8][CH][2] | s_inv[CH] | s_c[CH]
+    //   | s_zi[CH] | s_zp[CH] | s_lu[CH] | s_u[CH] | (floats) sd[D] | mean[n_stored][D] | cdf[n_cols]
     R* th_all = reinterpret_cast<R*>(smem_raw);
-    R* xs_all = th_all + (size_t)kDkChains * S;
-    R* ring_all = xs_all + (size_t)kDkChains * S;
+    R* xs_all = th_all + (size_t)CH * S;
+    R* ring_all = xs_all + (size_t)CH * S;
     R* red = ring_all + (size_t)kDkWarps * kDkDepth * NT * 32;
-    R* s_inv = red + kDkWarps * kDkChains * 2;
-    R* s_c = s_inv + kDkChains;
-    R* s_zi = s_c + kDkChains;
-    R* s_zp = s_zi + kDkChains;
-    R* s_u = s_zp + kDkChains;
-    float* s_sd = reinterpret_cast<float*>(s_u + kDkChains);
+    R* s_inv = red + kDkWarps * CH * 2;
+    R* s_c = s_inv + CH;
+    R* s_zi = s_c + CH;
+    R* s_zp = s_zi + CH;
+    R* s_lu = s_zp + CH;
+    R* s_u = s_lu + CH;
+    float* s_sd = reinterpret_cast<float*>(s_u + CH);
     float* s_mean = s_sd + D;
     float* s_cdf = s_mean + (size_t)n_stored * D;
     R* th = th_all + (size_t)o * S;
     R* xs = xs_all + (size_t)o * S;
     R* ring = ring_all + (size_t)warp * kDkDepth * NT * 32;
 
-    const long long c = (long long)blockIdx.x * kDkChains + o;      // chain of this octet
+    const long long c = (long long)blockIdx.x * CH + o;             // chain of this lane group
     const bool valid = c < a.B;
-    const long long c_fit = (long long)blockIdx.x * kDkChains + tid; // chain fitted by thread tid < 32
+    const long long c_fit = (long long)blockIdx.x * CH + tid;       // chain fitted by thread tid < CH
     R* g_theta = reinterpret_cast<R*>(a.theta);
     const R* Lm = reinterpret_cast<const R*>(a.mp.p1);
 
@@ -148,15 +173,15 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
         for (int i = tid; i < n_stored * D; i += kDkThreads) s_mean[i] = (float)g_mean[i];
         for (int i = tid; i < n_cols; i += kDkThreads) s_cdf[i] = n_cols > 1 ? (float)reinterpret_cast<const R*>(a.dir.cdf)[i] : 1.0f;
     }
-    for (int i = j; i < S; i += kOct) {
+    for (int i = j; i < S; i += LPC) {
         th[i] = (valid && i < D) ? g_theta[c * D + i] : R(0);
         xs[i] = R(0);
     }
     __syncthreads();
 
     // w = L' theta for this thread's fragment positions (rows 8 m + r8, columns 8 tile_q + 2 k4 + e)
-    double wf[4][NT][2];
-    dk_tri_product<NT>(th_all, S, Lm, D, ring, warp, lane, wf);
+    double wf[MT][NT][2];
+    dk_tri_product<MT, NT>(th_all, S, Lm, D, ring, warp, lane, wf);
 
     const R tol = (R)a.fp.tol;
     const uint32_t k0s = (uint32_t)a.seed, k1s = (uint32_t)(a.seed >> 32);
@@ -167,22 +192,24 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
 
     for (int step = 0; step < a.n_steps; ++step) {
         const long long row = (long long)step * a.B + c;
-        // ---------------------------------------------------------------- A. variates and direction (octet per chain)
+        // ---------------------------------------------------------------- A. variates and direction (LPC lanes per chain)
         if (valid) {
             if constexpr (kReplay) {
                 const R* g_rho = reinterpret_cast<const R*>(a.rho);
-                for (int i = j; i < D; i += kOct) xs[i] = g_rho[c * D + i];
+                for (int i = j; i < D; i += LPC) xs[i] = g_rho[c * D + i];
                 if (j == 0) {
+                    const R u = reinterpret_cast<const R*>(a.u)[c];
                     s_inv[o] = R(1);
                     s_zi[o] = reinterpret_cast<const R*>(a.z_init)[c];
                     s_zp[o] = reinterpret_cast<const R*>(a.z_prop)[c];
-                    s_u[o] = reinterpret_cast<const R*>(a.u)[c];
+                    s_u[o] = u;
+                    s_lu[o] = r_log(u);
                 }
             } else {
                 const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
                 const uint32_t d0 = (uint32_t)draw, k1d = k1s ^ (uint32_t)(draw >> 32);
                 // scalar variates (slots 0..2, same mapping as chain_scalars): lanes 0..2 expand one slot each
-                R sv0 = 0, sv1 = 0;
+                R sv0 = 0;
                 if (j < 3) {
                     uint32_t wv[4];
                     Philox::block(c0, c1, d0, (uint32_t)j, k0s, k1d, wv);
@@ -190,26 +217,26 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
                         float z0, z1;
                         box_muller_f32(wv[2], wv[3], z0, z1);
                         sv0 = (R)u01_32(wv[0]);
-                        sv1 = (R)z0;
+                        s_zi[o] = (R)z0;
                     } else if (j == 1) {
-                        sv0 = box_muller_f64(u01_53(wv[0], wv[1]), u01_53(wv[2], wv[3]));
+                        s_zp[o] = box_muller_f64(u01_53(wv[0], wv[1]), u01_53(wv[2], wv[3]));
                     } else {
-                        sv0 = u01_53(wv[0], wv[1]);
+                        const R u = u01_53(wv[0], wv[1]);
+                        s_u[o] = u;
+                        s_lu[o] = r_log(u);                    // log of the accept uniform, off the critical path of the fit
                     }
                 }
-                const R u_col = oct_bcast(sv0, 0, om);
+                const R u_col = __shfl_sync(0xffffffffu, sv0, 0, LPC);
                 int jcol = 0;
-                if (n_cols > 1)                            // searchsorted(cdf, u, 'right'), klhr.py:147
+                if (n_cols > 1)                                // searchsorted(cdf, u, 'right'), klhr.py:147
                     while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
-                if (j == 0) s_zi[o] = sv1;
-                if (j == 1) s_zp[o] = sv0;
-                if (j == 2) s_u[o] = sv0;
                 const float* mcol = (n_cols && jcol < n_stored) ? s_mean + (size_t)jcol * D : nullptr;
-                // element i = g0 + j + 32 t + 8 r  <->  Philox slot kSlotDir + j + 8 t + g0 / 4, word r
+                // element i = g0 + j8 + 32 t + 8 r  <->  Philox slot kSlotDir + j8 + 8 t + g0 / 4, word r
+                const int j8 = j & 7;
                 R ss = 0;
-                for (int g0 = 0; g0 < D; g0 += 128) {
+                for (int g0 = 128 * (j >> 3); g0 < D; g0 += 128 * (LPC / 8)) {
                     uint32_t wv[4][4];
-                    Philox::blockN<4>(c0, c1, d0, kSlotDir + (uint32_t)j + (uint32_t)(g0 / 4), 8u, k0s, k1d, wv);
+                    Philox::blockN<4>(c0, c1, d0, kSlotDir + (uint32_t)j8 + (uint32_t)(g0 / 4), 8u, k0s, k1d, wv);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         float z[4];
@@ -217,7 +244,7 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
                         box_muller_f32(wv[t][2], wv[t][3], z[2], z[3]);
 #pragma unroll
                         for (int rr = 0; rr < 4; ++rr) {
-                            const int i = g0 + j + 32 * t + 8 * rr;
+                            const int i = g0 + j8 + 32 * t + 8 * rr;
                             const R x = (R)fmaf(s_sd[i], z[rr], mcol ? mcol[i] : 0.0f);
                             xs[i] = x;
                             const R xt = x + tol;
@@ -225,16 +252,16 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
                         }
                     }
                 }
-                ss = oct_sum(ss, om);
+                ss = dk_grp_sum(ss);
                 if (j == 0) s_inv[o] = R(1) / r_sqrt(ss);      // rho = x / ||x + tol||  (klhr.py:153)
             }
         }
         __syncthreads();
         // ---------------------------------------------------------------- B. V = X L on the FP64 tensor cores
-        double vf[4][NT][2];
-        dk_tri_product<NT>(xs_all, S, Lm, D, ring, warp, lane, vf);
+        double vf[MT][NT][2];
+        dk_tri_product<MT, NT>(xs_all, S, Lm, D, ring, warp, lane, vf);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < MT; ++m) {
             double pa = 0, pb = 0;
 #pragma unroll
             for (int q = 0; q < NT; ++q)
@@ -248,31 +275,31 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
             pb += __shfl_xor_sync(0xffffffffu, pb, 1);
             pb += __shfl_xor_sync(0xffffffffu, pb, 2);
             if (k4 == 0) {
-                red[(warp * kDkChains + 8 * m + r8) * 2 + 0] = pa;
-                red[(warp * kDkChains + 8 * m + r8) * 2 + 1] = pb;
+                red[(warp * CH + 8 * m + r8) * 2 + 0] = pa;
+                red[(warp * CH + 8 * m + r8) * 2 + 1] = pb;
             }
         }
         __syncthreads();
         // ---------------------------------------------------------------- C. fit, proposal, MH (thread per chain)
-        if (tid < kDkChains) {
+        if (tid < CH) {
             R cmove = 0;
             if (c_fit < a.B) {
                 double sA = 0, sB = 0;
 #pragma unroll
                 for (int w8 = 0; w8 < kDkWarps; ++w8) {        // fixed order: deterministic
-                    sA += red[(w8 * kDkChains + tid) * 2 + 0];
-                    sB += red[(w8 * kDkChains + tid) * 2 + 1];
+                    sA += red[(w8 * CH + tid) * 2 + 0];
+                    sB += red[(w8 * CH + tid) * 2 + 1];
                 }
                 const R inv = s_inv[tid];
                 typename Model::Coef cf;
                 cf.A = __dmul_rn(__dmul_rn(sA, inv), inv);
                 cf.Bq = __dmul_rn(-sB, inv);
-                const R z_init = s_zi[tid], z_prop = s_zp[tid], u = s_u[tid];
+                const R z_init = s_zi[tid], z_prop = s_zp[tid];
                 StepOut<R> so;
-                if (!quad_fit_closed(cf.A, cf.Bq, z_init, z_prop, r_log(u), a.fp, a.tr.eta != nullptr, so)) {
+                if (!quad_fit_closed(cf.A, cf.Bq, z_init, z_prop, s_lu[tid], a.fp, a.tr.eta != nullptr, so)) {
                     OrCtx<R> oc;
                     oc.K = 0; oc.inject = false; oc.r = 0; oc.v = 1;
-                    fit_and_propose<1, R, Model, 2>(cf, a.fp, 0, 0u, z_init, R(0), R(0), z_prop, u, so, oc);
+                    fit_and_propose<1, R, Model, 2>(cf, a.fp, 0, 0u, z_init, R(0), R(0), z_prop, s_u[tid], so, oc);
                 }
                 cmove = so.accept ? __dmul_rn(so.zp, inv) : R(0);
                 n_acc += so.accept ? 1 : 0;
@@ -290,7 +317,7 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
                 if (!kReplay && a.tr.z_init) {
                     reinterpret_cast<R*>(a.tr.z_init)[trow] = z_init;
                     reinterpret_cast<R*>(a.tr.z_prop)[trow] = z_prop;
-                    reinterpret_cast<R*>(a.tr.u)[trow] = u;
+                    reinterpret_cast<R*>(a.tr.u)[trow] = s_u[tid];
                 }
             }
             s_c[tid] = cmove;
@@ -298,7 +325,7 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
         __syncthreads();
         // ---------------------------------------------------------------- D. move: theta += c x, w += c V
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < MT; ++m) {
             const R cm = s_c[8 * m + r8];
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
@@ -310,28 +337,38 @@ __global__ void __launch_bounds__(kDkThreads, 1) dense_kernel(const __grid_const
             if (a.tr.rho) {                                    // rho = x / ||x + tol|| (tests)
                 R* g = reinterpret_cast<R*>(a.tr.rho) + row * D;
                 const R inv = s_inv[o];
-                for (int i = j; i < D; i += kOct) g[i] = xs[i] * inv;
+                for (int i = j; i < D; i += LPC) g[i] = xs[i] * inv;
             }
             const R cm = s_c[o];
-            if (cm != R(0))
-                for (int i = j; i < D; i += kOct) th[i] = fma(cm, xs[i], th[i]);
+            if (cm != R(0)) {                                  // 128-bit accesses: the rows are 16-byte aligned (S even)
+                double2* t2 = reinterpret_cast<double2*>(th);
+                const double2* x2 = reinterpret_cast<const double2*>(xs);
+                for (int i = j; i < D / 2; i += LPC) {
+                    double2 t = t2[i];
+                    const double2 x = x2[i];
+                    t.x = fma(cm, x.x, t.x);
+                    t.y = fma(cm, x.y, t.y);
+                    t2[i] = t;
+                }
+            }
             if constexpr (kDraws) {
                 const long long gdraw = a.acc.thin_offset + step + 1;
                 if (gdraw % a.acc.thin == 0) {
                     R* g = reinterpret_cast<R*>(a.acc.draws) + ((gdraw / a.acc.thin - 1) * a.B + c) * D;
-                    for (int i = j; i < D; i += kOct) g[i] = th[i];
+                    for (int i = j; i < D; i += LPC) g[i] = th[i];
                 }
             }
         }
-        // no barrier: phase A of the next draw writes only this octet's own xs row and scalars, which nobody
+        // no barrier: phase A of the next draw writes only this group's own xs row and scalars, which nobody
         // else reads before the barrier that follows it; s_c / red are rewritten two barriers from here
     }
     if (valid)
-        for (int i = j; i < D; i += kOct) g_theta[c * D + i] = th[i];
-    if (tid < kDkChains) {
-        if (c_fit < a.B && a.acc.accept_count) a.acc.accept_count[c_fit] += n_acc;
+        for (int i = j; i < D; i += LPC) g_theta[c * D + i] = th[i];
+    if (tid < 32) {
+        const bool mine = tid < CH && c_fit < a.B;
+        if (mine && a.acc.accept_count) a.acc.accept_count[c_fit] += n_acc;
         if (a.acc.evals_total) {
-            unsigned long long tot = c_fit < a.B ? n_evals : 0ull;
+            unsigned long long tot = mine ? n_evals : 0ull;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
             if (tid == 0 && tot) atomicAdd(a.acc.evals_total, tot);
@@ -345,11 +382,10 @@ __host__ inline size_t densek_smem_bytes(const StepArgs& a, bool replay) {
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     size_t b = (size_t)2 * kDkChains * S * 8;                                  // theta, x
     b += (size_t)kDkWarps * kDkDepth * NT * 32 * 8;                            // cp.async rings
-    b += (size_t)(kDkWarps * kDkChains * 2 + 5 * kDkChains) * 8;               // red, inv, c, z_init, z_prop, u
+    b += (size_t)(kDkWarps * kDkChains * 2 + 6 * kDkChains) * 8;               // red, inv, c, z_init, z_prop, log u, u
     b += (size_t)(D + (size_t)n_stored * D + ((n_cols + 3) & ~3)) * 4;         // sd, mean columns, cdf
     return b;
 }
-
 // fp64, Gaussian family, no in-kernel accumulators, standard proposals, Cholesky factor supplied, D = 128 | 256
 __host__ inline bool densek_applies(const StepArgs& a, int dtype, int family, bool replay, bool accum, int flags) {
     return !(flags & KLHR_FIT_FORCE_OCTET) && dtype == KLHR_F64 && family == KLHR_FAMILY_GAUSS && !accum &&

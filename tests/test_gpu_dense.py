@@ -19,7 +19,8 @@ def test_dense_kernel_is_dispatched_and_replays_the_oracle(N, rho):
     model = kb.BSModel(stan_file="stan/corr-normal.stan", data=data, device=device())
     kfit, _ = fit_pair("gauss")
     info = kb.launch_info(model, kfit, dtype=torch.float64, free_running=True, accumulate=False, device=device())
-    assert info["threads"] == 256 and info["ctas_per_sm"] == 1 and info["smem"] > 150_000     # the dense kernel
+    want_smem = 2 * 32 * (N + 4) * 8 + 8 * 8 * (N // 64) * 32 * 8 + (8 * 32 * 2 + 6 * 32) * 8 + N * 4
+    assert info["threads"] == 256 and info["ctas_per_sm"] == 1 and info["smem"] == want_smem    # the dense kernel
     rng = np.random.default_rng(N)
     for B in (1, 77, 1000):                                   # ragged last CTA (32 chains per CTA)
         theta = rng.normal(size=(B, N)) * 0.7
@@ -80,5 +81,5 @@ def test_dense_kernel_thinned_draws_match_octet_kernel():
         assert abs(s.acceptance_probability - 1.0) < 1e-12     # Gaussian target, Gaussian family: always accepted
         out.append(rows)
     scale = float(out[1].abs().max())
-    assert float((out[0] - out[1]).abs().max()) <= 1e-8 * scale
+    assert float((out[0] - out[1]).abs().max()) <= 1e-7 * scale
     assert float((out[0][1] - out[0][0]).abs().max()) > 0
