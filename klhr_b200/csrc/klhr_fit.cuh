@@ -110,7 +110,8 @@ struct KLState {
 // Solve (H) p = -g by Cholesky, entry by entry like oracle/batched.py:_chol_solve.
 template <typename R, int n>
 __device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R (&g)[n], R (&p)[n]) {
-    // one division per pivot (its reciprocal), multiplications everywhere else
+    // one reciprocal square root per pivot, multiplications everywhere else: the diagonal of L is never needed, only
+    // its reciprocal (sqrt followed by a division was a quarter of the dependent-latency chain of a Newton step)
     R L[n][n], iL[n];
     bool ok = true;
 #pragma unroll
@@ -119,9 +120,7 @@ __device__ __forceinline__ bool chol_solve(const R (&H)[n][n], R shift, const R 
 #pragma unroll
         for (int k = 0; k < j; ++k) acc = acc - L[j][k] * L[j][k];
         ok = ok && (acc > R(0));
-        const R ljj = r_sqrt(acc > R(0) ? acc : R(1));
-        L[j][j] = ljj;
-        iL[j] = R(1) / ljj;
+        iL[j] = r_rsqrt(acc > R(0) ? acc : R(1));
 #pragma unroll
         for (int i = j + 1; i < n; ++i) {
             R a2 = H[i][j];
@@ -183,9 +182,11 @@ __device__ __forceinline__ void newton_direction(const KLState<R, n>& S, const F
         big = r_max(big, r_abs(p[i]));
     }
     const R cap = (R)fp.step_cap;
-    const R scale = big > cap ? cap / big : R(1);
+    if (big > cap) {                               // rare: keeps the division off the common path
+        const R scale = cap / big;
 #pragma unroll
-    for (int i = 0; i < n; ++i) p[i] = p[i] * scale;
+        for (int i = 0; i < n; ++i) p[i] = p[i] * scale;
+    }
 }
 
 // ------------------------------------------------------------------ KL objective, Gaussian family
@@ -274,15 +275,22 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
     const R invd = R(1) / q.d;
     R f = 0, g1 = 0, g2 = 0, g3 = 0, g0 = 0;
     R h00 = 0, h01 = 0, h02 = 0, h03 = 0, h11 = 0, h12 = 0, h13 = 0, h22 = 0, h23 = 0, h33 = 0;
+#ifndef KLHR_KL_UNROLL
+#define KLHR_KL_UNROLL 1
+#endif
+    constexpr int kUnroll = G == 1 ? KLHR_KL_UNROLL : 1;
+#pragma unroll(kUnroll)
     for (int n = lane; n < fp.N; n += G) {
         const R w = (R)fp.w[n];
         const R a = ((R)fp.cx[n] + q.e) * invd;
         const R ac = r_clamp(a, -c, c);
         // sinh, cosh, tanh and log cosh from ONE exponential (|ac| <= scale_clip = 300 keeps e^ac
         // finite in fp64); absolute accuracy ~1 ulp of cosh, which is what T and the KL sums need
-        const R E = r_exp(ac), Ei = R(1) / E;
+        // e^-ac by a second exponential (independent of the first: the two overlap) instead of a division, and
+        // tanh through a Newton reciprocal of cosh (1 <= cosh <= e^300 / 2: no special cases to guard)
+        const R E = r_exp(ac), Ei = r_exp(-ac);
         const R sh = R(0.5) * (E - Ei), ch = R(0.5) * (E + Ei);
-        const R th = sh / ch;
+        const R th = sh * r_rcp_normal(ch);
         const R sech2 = R(1) - th * th;
         const R T = q.m + q.s * sh;
         R l1c;                                                                    // l' with the elementwise clip
