@@ -9,7 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-B, D, WARM, EXTRA = 8192, 24, 100, 40
+B, D, WARM, EXTRA = 8192, 24, 200, 40
 
 
 def _make(kb, dev, chains, group=None, chain_offset=None, cls="KLHR"):
@@ -45,7 +45,7 @@ def test_two_ranks_nccl_equal_one_rank_bitwise(tmp_path, cls):
     mp.spawn(_rank_worker, args=(2, port, out, cls), nprocs=2, join=True)
     r = [torch.load(f"{out}.{k}", weights_only=False) for k in range(2)]
     one = _make(kb, torch.device("cuda", 0), B, chain_offset=0, cls=cls)
-    assert one._windowedadaptation.closures == [25, 75, 100]
+    assert one._windowedadaptation.closures == [25, 75, 200]        # three closures = three collectives
     one.run(WARM + EXTRA)
     # adaptation state: identical on both ranks and identical to the unsharded run
     for k in ("cov", "eigvecs", "eigvals", "mean"):
