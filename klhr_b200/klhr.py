@@ -327,6 +327,10 @@ class KLHR(MCMCBase):
         if not chain_stats:
             self._advance(n)
             return None
+        if self._moments_every_draw and self._windowedadaptation.next_closure(self._draw) is not None:
+            # the kernel has ONE accumulator slot per chain: during warm-up it belongs to the per-draw adaptation moments
+            raise RuntimeError("chain_stats during warm-up needs moments_every_draw=False (the per-draw warm-up "
+                               "accumulation uses the kernel's accumulator slot); finish the warm-up first")
         s1 = torch.zeros(self.chains, self.D, dtype=torch.float64, device=self.device)
         s2 = torch.zeros_like(s1)
         self._advance(n, chain_s1=s1, chain_s2=s2, stat_shift=None)
