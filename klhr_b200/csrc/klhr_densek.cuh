@@ -49,9 +49,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ int dk_tile(int q, int w) { return (q & 1) ? 8 * (q - 1) + 15 - w : 8 * q + w; }
 
 // acc[m][q][e] (m < MT row tiles) = sum_k rows[8 m + r8][k] * L[k][8 tile_q + 2 k4 + e]   (k >= 8 tile_q: L is lower triangular)
-// rows: [8 MT][S] in shared memory; ring: this warp's [kDkDepth][NT][32] staging doubles.
-template <int MT, int NT>
-__device__ __forceinline__ void dk_tri_product(const double* __restrict__ rows, int S, const double* __restrict__ Lm, int D,
+// rows: [8 MT][S] (double or float) in shared memory; ring: this warp's [DEPTH][NT][32] staging doubles.
+template <int MT, int NT, typename XT = double, int DEPTH = kDkDepth>
+__device__ __forceinline__ void dk_tri_product(const XT* __restrict__ rows, int S, const double* __restrict__ Lm, int D,
                                                double* ring, int warp, int lane, double (&acc)[MT][NT][2]) {
     const int r8 = lane >> 2, k4 = lane & 3;
 #pragma unroll
@@ -81,11 +81,11 @@ __device__ __forceinline__ void dk_tri_product(const double* __restrict__ rows, 
         }
         cp_async_commit();
         ++i_issue;
-        slot_w = (slot_w + 1) & (kDkDepth - 1);
+        slot_w = (slot_w + 1) & (DEPTH - 1);
     };
 #pragma unroll
-    for (int i = 0; i < kDkDepth - 1; ++i) issue();
-    const double* ar = rows + (size_t)r8 * S + k4 + kb;
+    for (int i = 0; i < DEPTH - 1; ++i) issue();
+    const XT* ar = rows + (size_t)r8 * S + k4 + kb;
     const size_t s8 = (size_t)8 * S;
     int slot_r = 0;
     auto segment = [&](auto na_tag, int i_begin, int i_end) {
@@ -93,12 +93,12 @@ __device__ __forceinline__ void dk_tri_product(const double* __restrict__ rows, 
 #pragma unroll 2
         for (int i = i_begin; i < i_end; ++i) {
             issue();
-            cp_async_wait<kDkDepth - 1>();
+            cp_async_wait<DEPTH - 1>();
             const double* slot = my_ring + slot_r * (NT * 32);
-            slot_r = (slot_r + 1) & (kDkDepth - 1);
+            slot_r = (slot_r + 1) & (DEPTH - 1);
             double av[MT], bv[NA];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) av[m] = ar[m * s8];
+            for (int m = 0; m < MT; ++m) av[m] = (double)ar[m * s8];
             ar += 4;
 #pragma unroll
             for (int q = 0; q < NA; ++q) bv[q] = slot[q * 32];
