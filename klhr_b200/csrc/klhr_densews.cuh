@@ -3,22 +3,24 @@
 // re-timed: there, one set of 8 warps alternates between the tensor-core phase (46 % of a draw) and the scalar phases
 // (direction 24 %, move 18 %, fit 7 %), and since a warp issues in order its own scalar work cannot hide under its own
 // DMMAs.  Here the roles are split over warps, which the schedulers interleave for free:
-//   * 8 TENSOR warps per CTA: V(t) = X(t) L, fold (A, Bq partial sums), then -- while the fit of draw t runs -- the
-//     move of draw t-1 (theta += c(t-1) x(t-1)), then w += c(t) V(t);
-//   * 4 PRODUCER warps: draw X(t+1) and the scalar variates of draw t+1 (Philox + Box-Muller, 4 lanes per chain) while
-//     the tensor warps work on X(t); the first of them also runs the closed-form fit of draw t (one thread per chain)
-//     as soon as the partial sums are in.
-// X is fp32 (the directions ARE fp32 values: fmaf(sd, z, mean)) in THREE buffers: X(t) is multiplied, X(t+1) is being
-// drawn, X(t-1) is still needed by the pending move.  One CTA-wide barrier per draw hands the buffers over; two
-// partial barriers (bar.arrive / bar.sync on 288 threads) pass the sums to the fit and the result back.
+//   * 8 TENSOR warps per CTA: V(t) = X(t) L, fold (A, Bq partial sums), w += c(t) V(t).  Their w = L' theta lives in shared
+//     memory in the fragment layout's home positions (each thread only ever touches its own 32 entries, and only
+//     between the product and the update), so that the product loop has the registers to keep loads, converts and
+//     DMMAs of neighbouring k-steps in flight;
+//   * 4 PRODUCER warps (4 lanes per chain): under the product on X(t) they apply the move of draw t-1 (theta += c x, theta
+//     in global memory / L2: nothing else on the device reads it), draw X(t+1) and the scalar variates of draw t+1
+//     (Philox + Box-Muller) into the buffer the move has just released; the first of them also runs the closed-form fit
+//     of draw t (one thread per chain) as soon as the partial sums are in.
+// X is fp32 (the directions ARE fp32 values: fmaf(sd, z, mean)) in two buffers.  One CTA-wide barrier per draw hands the
+// buffers over; two partial barriers (bar.arrive / bar.sync on 288 threads) pass the sums to the fit and c back.
 #pragma once
 #include "klhr_densek.cuh"
 
 namespace klhr {
 
 constexpr int kWsTensor = 256, kWsProducer = 128, kWsThreads = kWsTensor + kWsProducer;
-constexpr int kWsDepth = 4;                        // k-steps of L in flight per tensor warp (three X buffers take the room)
-constexpr int kWsBuf = 3;
+constexpr int kWsDepth = 8;                        // k-steps of L in flight per tensor warp
+constexpr int kWsBuf = 2;
 
 __device__ __forceinline__ void ws_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void ws_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -30,15 +32,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
     constexpr int CH = 32, MT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.mp.D;
-    const int S = D + 4;                               // pitch of theta (doubles) and of X (floats): both conflict-free
+    const int S = D + 4;                               // pitch of X (floats) and of the theta staging rows (doubles): conflict-free A fragments
+    const int SW = D + 8;                              // pitch of w (doubles): conflict-free 128-bit fragment accesses
     const int tid = threadIdx.x;
     const bool tensor = tid < kWsTensor;
     const int n_cols = a.dir.mean_cols ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
-    // shared memory: th[CH][S] (double) | ring[8][depth][NT][32] | red[8][CH][2] | s_c[2][CH] | var[3][5][CH]
-    //   | (floats) xf[3][CH][S] | sd[D] | mean[n_stored][D] | cdf[n_cols]
-    R* th_all = reinterpret_cast<R*>(smem_raw);
-    R* ring_all = th_all + (size_t)CH * S;
+    // shared memory: w[CH][SW] (double) | ring[8][depth][NT][32] | red[8][CH][2] | s_c[2][CH] | var[2][5][CH]
+    //   | (floats) xf[2][CH][S] (= one [CH][S] double tile while w is initialised) | sd[D] | mean[n_stored][D] | cdf[n_cols]
+    R* w_all = reinterpret_cast<R*>(smem_raw);
+    R* ring_all = w_all + (size_t)CH * SW;
     R* red = ring_all + (size_t)8 * kWsDepth * NT * 32;
     R* s_c = red + 8 * CH * 2;
     R* s_var = s_c + 2 * CH;                           // per buffer: inv, z_init, z_prop, log u, u
@@ -55,15 +58,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
         for (int i = tid; i < D; i += kWsThreads) s_sd[i] = g_sd ? (float)g_sd[i] : 1.0f;
         for (int i = tid; i < n_stored * D; i += kWsThreads) s_mean[i] = (float)g_mean[i];
         for (int i = tid; i < n_cols; i += kWsThreads) s_cdf[i] = n_cols > 1 ? (float)reinterpret_cast<const R*>(a.dir.cdf)[i] : 1.0f;
-        for (int i = tid; i < kWsBuf * CH * S; i += kWsThreads) xf_all[i] = 0.0f;
+        R* th_stage = reinterpret_cast<R*>(xf_all);    // theta rows, only to form w = L' theta
         for (int i = tid; i < CH * S; i += kWsThreads) {
             const int rr = i / S, cc = i - rr * S;
-            th_all[i] = (chain0 + rr < a.B && cc < D) ? g_theta[(chain0 + rr) * D + cc] : R(0);
+            th_stage[i] = (chain0 + rr < a.B && cc < D) ? g_theta[(chain0 + rr) * D + cc] : R(0);
         }
     }
     __syncthreads();
     const R tol = (R)a.fp.tol;
     const uint32_t k0s = (uint32_t)a.seed, k1s = (uint32_t)(a.seed >> 32);
+    // w = L' theta, written out in the fragment layout's home positions (row 8 m + r8, columns 8 tile_q + 2 k4 + {0, 1})
+    if (tensor) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int r8 = lane >> 2, k4 = lane & 3;
+        double wf[MT][NT][2];
+        dk_tri_product<MT, NT, double, kWsDepth>(reinterpret_cast<const R*>(xf_all), S, Lm, D,
+                                                 ring_all + (size_t)warp * kWsDepth * NT * 32, warp, lane, wf);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+                *reinterpret_cast<double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4) = make_double2(wf[m][q][0], wf[m][q][1]);
+    }
+    __syncthreads();
+    for (int i = tid; i < kWsBuf * CH * S; i += kWsThreads) xf_all[i] = 0.0f;
+    __syncthreads();
 
     if (tensor) {
         // ============================================================ tensor warps
@@ -71,25 +90,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
         const int o = tid >> 3, j = tid & 7;
         const int r8 = lane >> 2, k4 = lane & 3;
         const bool valid = chain0 + o < a.B;
-        R* th = th_all + (size_t)o * S;
         R* ring = ring_all + (size_t)warp * kWsDepth * NT * 32;
-        double wf[MT][NT][2];                          // w = L' theta at this thread's fragment positions
-        dk_tri_product<MT, NT, double, kWsDepth>(th_all, S, Lm, D, ring, warp, lane, wf);
         for (int step = 0; step < a.n_steps; ++step) {
-            __syncthreads();                           // X(step) drawn; buffer (step + 1) % 3 free; c(step - 1) applied to w
-            const int cur = step % kWsBuf;
+            __syncthreads();                           // X(step) drawn; c(step - 1) applied to w
+            const int cur = step & 1;
             double vf[MT][NT][2];
             dk_tri_product<MT, NT, float, kWsDepth>(xf_all + (size_t)cur * CH * S, S, Lm, D, ring, warp, lane, vf);
+            double2 wfr[MT][NT];                       // this thread's fragments of w: live from here to the update below only
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 double pa = 0, pb = 0;
 #pragma unroll
-                for (int q = 0; q < NT; ++q)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        pa = fma(vf[m][q][e], vf[m][q][e], pa);
-                        pb = fma(wf[m][q][e], vf[m][q][e], pb);
-                    }
+                for (int q = 0; q < NT; ++q) {
+                    wfr[m][q] = *reinterpret_cast<const double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4);
+                    pa = fma(vf[m][q][0], vf[m][q][0], pa);
+                    pb = fma(wfr[m][q].x, vf[m][q][0], pb);
+                    pa = fma(vf[m][q][1], vf[m][q][1], pa);
+                    pb = fma(wfr[m][q].y, vf[m][q][1], pb);
+                }
                 pa += __shfl_xor_sync(0xffffffffu, pa, 1);
                 pa += __shfl_xor_sync(0xffffffffu, pa, 2);
                 pb += __shfl_xor_sync(0xffffffffu, pb, 1);
@@ -100,61 +118,58 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
                 }
             }
             ws_bar_arrive(1, kWsTensor + 32);          // the sums of draw `step` are in: the fit may start
-            // while it runs: the move of the previous draw, theta += c(step - 1) x(step - 1)
-            if (valid && step > 0) {
-                const R cm = s_c[((step - 1) & 1) * CH + o];
-                if (cm != R(0)) {
-                    const float2* x2 = reinterpret_cast<const float2*>(xf_all + ((size_t)((step - 1) % kWsBuf) * CH + o) * S);
-                    double2* t2 = reinterpret_cast<double2*>(th);
-                    for (int i = j; i < D / 2; i += kOct) {
-                        double2 t = t2[i];
-                        const float2 x = x2[i];
-                        t.x = fma(cm, (double)x.x, t.x);
-                        t.y = fma(cm, (double)x.y, t.y);
-                        t2[i] = t;
-                    }
-                }
-            }
             if (valid && a.tr.rho) {                   // rho = x / ||x + tol|| (tests)
                 R* g = reinterpret_cast<R*>(a.tr.rho) + ((long long)step * a.B + chain0 + o) * D;
                 const float* xc = xf_all + ((size_t)cur * CH + o) * S;
                 const R inv = s_var[(size_t)cur * 5 * CH + o];
                 for (int i = j; i < D; i += kOct) g[i] = (R)xc[i] * inv;
             }
-            ws_bar_sync(2, kWsTensor + 32);            // c(step) is known
+            ws_bar_sync(2, kWsTensor + 32);            // c(step) is known: w += c V
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const R cm = s_c[(step & 1) * CH + 8 * m + r8];
 #pragma unroll
                 for (int q = 0; q < NT; ++q) {
-                    wf[m][q][0] = fma(cm, vf[m][q][0], wf[m][q][0]);
-                    wf[m][q][1] = fma(cm, vf[m][q][1], wf[m][q][1]);
+                    double2 t = wfr[m][q];
+                    t.x = fma(cm, vf[m][q][0], t.x);
+                    t.y = fma(cm, vf[m][q][1], t.y);
+                    *reinterpret_cast<double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4) = t;
                 }
             }
         }
         __syncthreads();
-        if (valid) {                                   // the move of the last draw, then write back
-            const int last = a.n_steps - 1;
-            const R cm = a.n_steps > 0 ? s_c[(last & 1) * CH + o] : R(0);
-            const float* xl = xf_all + ((size_t)((last < 0 ? 0 : last) % kWsBuf) * CH + o) * S;
-            for (int i = j; i < D; i += kOct) g_theta[(chain0 + o) * D + i] = fma(cm, (double)xl[i], th[i]);
-        }
     } else {
         // ============================================================ producer warps
         const int ptid = tid - kWsTensor;
         const int pc = ptid >> 2, q4 = ptid & 3;       // chain slot, lane of its group of 4
         const bool pvalid = chain0 + pc < a.B;
+        const unsigned gmask = 0xFu << (4 * ((ptid & 31) >> 2));   // the 4 lanes of this chain (validity is uniform over them)
         const unsigned long long cid = (unsigned long long)(a.chain_offset + chain0 + pc);
         const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
-        const unsigned gmask = 0xFu << (4 * ((ptid & 31) >> 2));   // the 4 lanes of this chain (validity is uniform over them)
         const bool fitter = ptid < 32;                 // the first producer warp also fits: thread ptid <-> chain ptid
         const long long c_fit = chain0 + ptid;
         long long n_acc = 0;
         unsigned long long n_evals = 0;
+        double2* th2 = reinterpret_cast<double2*>(g_theta + (chain0 + pc) * D);     // D even: rows are 16-byte aligned
 
-        auto draw_direction = [&](int step) {          // X(step) and the scalar variates of draw `step` into buffer step % 3
+        // theta += c(step) x(step): theta lives in global memory (L2) -- only this move and the caller ever touch it
+        auto move = [&](int step) {
             if (!pvalid) return;
-            const int nb = step % kWsBuf;
+            const R cm = s_c[(step & 1) * CH + pc];
+            if (cm == R(0)) return;
+            const float2* x2 = reinterpret_cast<const float2*>(xf_all + ((size_t)(step & 1) * CH + pc) * S);
+#pragma unroll 8
+            for (int i = q4; i < D / 2; i += 4) {
+                double2 t = th2[i];
+                const float2 x = x2[i];
+                t.x = fma(cm, (double)x.x, t.x);
+                t.y = fma(cm, (double)x.y, t.y);
+                th2[i] = t;
+            }
+        };
+        auto draw_direction = [&](int step) {          // X(step) and the scalar variates of draw `step` into buffer step & 1
+            if (!pvalid) return;
+            const int nb = step & 1;
             float* xn = xf_all + ((size_t)nb * CH + pc) * S;
             R* var = s_var + (size_t)nb * 5 * CH;
             const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
@@ -209,13 +224,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
             if (q4 == 0) var[pc] = R(1) / r_sqrt(ss);  // rho = x / ||x + tol||  (klhr.py:153)
         };
 
-        if (a.n_steps > 0) draw_direction(0);          // under the tensor warps' w = L' theta
+        if (a.n_steps > 0) draw_direction(0);
         for (int step = 0; step < a.n_steps; ++step) {
             __syncthreads();
+            // under the tensor warps' product on X(step): the move of draw step - 1 (its direction sits in the buffer that
+            // X(step + 1) is about to overwrite -- same lanes, program order), then X(step + 1)
+            if (step > 0) move(step - 1);
             if (step + 1 < a.n_steps) draw_direction(step + 1);
             if (fitter) {
                 ws_bar_sync(1, kWsTensor + 32);        // sums of draw `step`
-                const R* var = s_var + (size_t)(step % kWsBuf) * 5 * CH;
+                const R* var = s_var + (size_t)(step & 1) * 5 * CH;
                 R cmove = 0;
                 if (c_fit < a.B) {
                     double sA = 0, sB = 0;
@@ -259,6 +277,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
             }
         }
         __syncthreads();
+        if (a.n_steps > 0) move(a.n_steps - 1);        // the move of the last draw
         if (fitter) {
             const bool mine = c_fit < a.B;
             if (mine && a.acc.accept_count) a.acc.accept_count[c_fit] += n_acc;
@@ -273,13 +292,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
 }
 
 __host__ inline size_t densews_smem_bytes(const StepArgs& a) {
-    const int D = a.mp.D, S = D + 4, NT = D / 64;
+    const int D = a.mp.D, S = D + 4, SW = D + 8, NT = D / 64;
     const int n_cols = a.dir.mean_cols ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
-    size_t b = (size_t)32 * S * 8;                                             // theta
+    size_t b = (size_t)32 * SW * 8;                                            // w = L' theta
     b += (size_t)8 * kWsDepth * NT * 32 * 8;                                   // cp.async rings
-    b += (size_t)(8 * 32 * 2 + 2 * 32 + kWsBuf * 5 * 32) * 8;                  // red, c (two draws), variates (three buffers)
-    b += (size_t)kWsBuf * 32 * S * 4;                                          // X, three fp32 buffers
+    b += (size_t)(8 * 32 * 2 + 2 * 32 + kWsBuf * 5 * 32) * 8;                  // red, c (two draws), variates (two buffers)
+    b += (size_t)kWsBuf * 32 * S * 4;                                          // X, two fp32 buffers (= the theta staging tile)
     b += (size_t)(D + (size_t)n_stored * D + ((n_cols + 3) & ~3)) * 4;         // sd, mean columns, cdf
     return b;
 }
