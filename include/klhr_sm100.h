@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KLHR_ABI_VERSION 3
+#define KLHR_ABI_VERSION 4
 
 enum { KLHR_F64 = 0, KLHR_F32 = 1 };
 enum { KLHR_FAMILY_GAUSS = 0, KLHR_FAMILY_SINH = 1 };
@@ -36,8 +36,8 @@ enum {
     KLHR_MODEL_ILL_NORMAL = 1,  /* stan/ill-normal.stan   data0 = inv_s2[D]                       */
     KLHR_MODEL_FUNNEL = 2,      /* stan/funnel.stan       i0 = D (number of alpha); dim = D + 1   */
     KLHR_MODEL_CORR_NORMAL = 3, /* stan/corr-normal.stan  data0 = dense precision P[D*D]; data1 (optional, fp64) =
-                                   lower Cholesky factor L[D*D] of P, row-major, zeros above the diagonal:
-                                   enables the triangular tensor-core kernel for D = 128 / 256             */
+                                   the lower Cholesky factor of P packed by klhr_corr_pack_cholesky: enables
+                                   the triangular tensor-core kernels for D = 128 / 256                    */
     KLHR_MODEL_AR1 = 4,         /* stan/ar1.stan          s0 = alpha, s1 = 1/beta^2               */
     KLHR_MODEL_ARK = 5,         /* stan/arK.stan          i0 = K, i1 = T-K, data0 = [G|c|yy]      */
     KLHR_MODEL_ROSENBROCK = 6,  /* stan/rosenbrock.stan   i0 = D; dim = 2 D                       */
@@ -250,6 +250,13 @@ int klhr_outer_reduce(double* scratch_dev, int64_t scratch_doubles, double* oute
  * kernel would be launched with for this problem; returns resident CTAs per SM (<=0 error). */
 int klhr_launch_info(const klhr_model_t* model, const klhr_fit_t* fit, int dtype, int free_running,
                      int accumulate, int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* regs);
+
+/* Host helper for klhr_model_t.data1 of KLHR_MODEL_CORR_NORMAL: packs the lower Cholesky factor L (host, row-major
+ * [dim][dim], P = L L') into the order the tensor-core kernels consume it -- for column tile nt = 0 .. dim/8 - 1, for
+ * k-pair p = nt .. dim/8 - 1, for lane = 0 .. 31 (r8 = lane / 4, k4 = lane % 4): L[8 p + k4][8 nt + r8] and
+ * L[8 p + 4 + k4][8 nt + r8] (the zero part of the triangle is not stored).  Returns the number of doubles of the packed
+ * stream (out_host may be NULL to query it), or < 0 unless dim is 128 or 256.  The caller copies the stream to the device. */
+int64_t klhr_corr_pack_cholesky(const double* L_host, int32_t dim, double* out_host);
 
 /* Test hook: out[i][0..3] = Philox4x32-10(counter = in[i][0..3], key = in[i][4..5]) with the generator the step
  * kernels use (csrc/klhr_common.cuh), for the Random123 known-answer vectors (tests/test_gpu_philox.py). */

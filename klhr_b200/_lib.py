@@ -16,7 +16,7 @@ LIB_PATH = _HERE / "libklhr_sm100.so"
 KLHR_F64, KLHR_F32 = 0, 1
 FAMILY_GAUSS, FAMILY_SINH = 0, 1
 MAX_NODES = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MODEL_IDS = {"normal": 0, "ill-normal": 1, "funnel": 2, "corr-normal": 3, "ar1": 4, "arK": 5,
              "rosenbrock": 6, "earnings": 7}
@@ -86,6 +86,7 @@ EXPORTS = {
                                         C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_outer_scratch_doubles": (C.c_int64, [C.c_int64, C.c_int32]),
     "klhr_outer_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "klhr_corr_pack_cholesky": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p]),
     "klhr_philox_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "klhr_peak_probe": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "klhr_launch_info": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(FitDesc), C.c_int, C.c_int, C.c_int,

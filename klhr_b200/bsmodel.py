@@ -70,8 +70,17 @@ class BSModel:
             Sigma = rho ** np.abs(idx[:, None] - idx[None, :])
             P = np.linalg.inv(Sigma)
             P = 0.5 * (P + P.T)
-            # P = L L' (fp64): the dense kernel works with V = L' rho and w = L' theta (csrc/klhr_densek.cuh)
-            h.update(dim=N, data0=P.reshape(-1), data1=np.tril(np.linalg.cholesky(P)).reshape(-1))
+            h.update(dim=N, data0=P.reshape(-1))
+            if N in (128, 256):
+                # P = L L' (fp64): the dense kernels work with V = L' rho and w = L' theta (csrc/klhr_densek.cuh); L goes
+                # to the device packed in the order the tensor warps consume it (klhr_corr_pack_cholesky)
+                L = np.ascontiguousarray(np.tril(np.linalg.cholesky(P)), dtype=np.float64)
+                lib = _lib.load()
+                n = lib.klhr_corr_pack_cholesky(None, N, None)
+                packed = np.empty(int(n), dtype=np.float64)
+                if lib.klhr_corr_pack_cholesky(L.ctypes.data, N, packed.ctypes.data) != n:
+                    raise _lib.KLHRLibraryError(f"klhr_corr_pack_cholesky failed: {_lib.last_error()}")
+                h["data1"] = packed
         elif n == "ar1":                             # stan/ar1.stan:4-7
             alpha = 0.9
             h.update(dim=int(d["N"]), s0=alpha, s1=1.0 / (1.0 - alpha * alpha))

@@ -543,6 +543,30 @@ static void outer_slicing(int64_t n_chains, int32_t dim, int& tiles, long long& 
     if (slices < 1) slices = 1;
 }
 
+int64_t klhr_corr_pack_cholesky(const double* L_host, int32_t dim, double* out_host) {
+    if (dim != 128 && dim != 256) {
+        fail(-3, "klhr_corr_pack_cholesky: the tensor-core kernels take dim = 128 or 256");
+        return -3;
+    }
+    const int T = dim / 8;
+    if (out_host) {
+        if (!L_host) {
+            fail(-1, "klhr_corr_pack_cholesky: L_host is NULL");
+            return -1;
+        }
+        for (int nt = 0; nt < T; ++nt) {
+            double* o = out_host + dk_pack_offset(nt, T);
+            for (int p = nt; p < T; ++p)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int r8 = lane >> 2, k4 = lane & 3;
+                    *o++ = L_host[(size_t)(8 * p + k4) * dim + 8 * nt + r8];
+                    *o++ = L_host[(size_t)(8 * p + 4 + k4) * dim + 8 * nt + r8];
+                }
+        }
+    }
+    return (int64_t)dk_pack_doubles(dim);
+}
+
 int64_t klhr_outer_scratch_doubles(int64_t n_chains, int32_t dim) {
     if (n_chains <= 0 || dim <= 0) return 0;
     int tiles;

@@ -14,11 +14,14 @@
 // DMMA counts for every warp although tile n only needs k >= 8 n), its accumulator fragments ARE V for those
 // columns, and the matching fragments of w stay in registers for the whole launch -- V and w are never written
 // to memory.  The B fragments of L stream L2 -> shared memory through a per-warp cp.async ring 8 k-steps deep
-// (each lane copies exactly the 8 bytes it will consume: no barrier, no bank conflict), so the L2 latency sits
+// (the factor is packed on the host in consumption order: each lane copies exactly the 16 bytes it will consume), so the L2 latency sits
 // behind 8 x 16 DMMAs.  The fit of a quadratic target is closed form (quad_fit_closed, klhr_lane.cuh); chains
 // whose premises fail take the generic iteration of klhr_fit.cuh, so every path returns the same iterates.
 // Variate streams are the same function of (seed, chain, draw, element) as in every other kernel.
 #pragma once
+#ifdef KLHR_DENSE_TIMING
+#include <cstdio>
+#endif
 #include "klhr_lane.cuh"
 
 namespace klhr {
@@ -32,91 +35,107 @@ namespace klhr {
 constexpr int kDkChains = KLHR_DENSEK_CHAINS;
 constexpr int kDkThreads = 256;
 constexpr int kDkWarps = kDkThreads / 32;
-constexpr int kDkDepth = kDkChains == 16 ? 4 : 8;  // k-steps of L in flight per warp (two CTAs per SM need <= 113 KB each)
+constexpr int kDkDepth = kDkChains == 16 ? 2 : 4;  // k-PAIRS (8 rows of L) in flight per warp (two CTAs per SM need <= 113 KB each)
 constexpr int kDkMT = kDkChains / 8;              // m8 row tiles
 constexpr int kDkLpc = kDkThreads / kDkChains;    // lanes per chain in the vector phases (8 or 16)
 static_assert(kDkChains == 16 || kDkChains == 32, "dense kernel: 16 or 32 chains per CTA");
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // column tile q (0..NT-1) of warp w: ascending in q, and sum_q tile = const for every warp
-__device__ __forceinline__ int dk_tile(int q, int w) { return (q & 1) ? 8 * (q - 1) + 15 - w : 8 * q + w; }
+__host__ __device__ __forceinline__ int dk_tile(int q, int w) { return (q & 1) ? 8 * (q - 1) + 15 - w : 8 * q + w; }
+
+// The Cholesky factor arrives PACKED in the order the tensor warps consume it (klhr_corr_pack_cholesky, klhr_api.cu;
+// klhr_model_t.data1): for column tile nt = 0 .. D/8 - 1, for k-pair p = nt .. D/8 - 1 (rows 8 p .. 8 p + 7: tile nt of
+// the lower-triangular L is zero above), for lane = 0 .. 31 (r8 = lane / 4, k4 = lane % 4) the two B-fragment values
+//     L[8 p + k4][8 nt + r8],  L[8 p + 4 + k4][8 nt + r8]
+// i.e. one 16-byte cp.async and one 128-bit shared load per lane feed the DMMAs of two k-steps, and the stream of a
+// tile is contiguous.  Offset of tile nt: 64 (nt T - nt (nt - 1) / 2) doubles, T = D / 8.
+__host__ __device__ __forceinline__ long long dk_pack_offset(int nt, int T) { return 64LL * ((long long)nt * T - (long long)nt * (nt - 1) / 2); }
+__host__ __device__ __forceinline__ long long dk_pack_doubles(int D) { return dk_pack_offset(D / 8, D / 8); }
 
 // acc[m][q][e] (m < MT row tiles) = sum_k rows[8 m + r8][k] * L[k][8 tile_q + 2 k4 + e]   (k >= 8 tile_q: L is lower triangular)
-// rows: [8 MT][S] (double or float) in shared memory; ring: this warp's [DEPTH][NT][32] staging doubles.
+// rows: [8 MT][S] (double or float) in shared memory; Lp: the packed factor; ring: this warp's [DEPTH][NT][32][2] staging doubles.
 template <int MT, int NT, typename XT = double, int DEPTH = kDkDepth>
-__device__ __forceinline__ void dk_tri_product(const XT* __restrict__ rows, int S, const double* __restrict__ Lm, int D,
+__device__ __forceinline__ void dk_tri_product(const XT* __restrict__ rows, int S, const double* __restrict__ Lp, int D,
                                                double* ring, int warp, int lane, double (&acc)[MT][NT][2]) {
     const int r8 = lane >> 2, k4 = lane & 3;
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int q = 0; q < NT; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-    int ist[NT];                                       // first k-step (relative to this warp's first tile) of tile q
-    const int kb = 8 * dk_tile(0, warp);
-    const double* gp[NT];                              // B-fragment source of tile q at the NEXT k-step to issue
+    const int T = D >> 3;
+    const int t0 = dk_tile(0, warp);
+    int ist[NT];                                       // first k-pair (relative to this warp's first tile) of tile q
+    const double* gp[NT];                              // source of tile q for the NEXT k-pair to issue (runs from before its stream)
 #pragma unroll
     for (int q = 0; q < NT; ++q) {
-        ist[q] = (8 * dk_tile(q, warp) - kb) >> 2;
-        gp[q] = Lm + (size_t)(kb + k4) * D + 8 * dk_tile(q, warp) + r8;
+        ist[q] = dk_tile(q, warp) - t0;
+        gp[q] = Lp + dk_pack_offset(dk_tile(q, warp), T) + 2 * lane - (long long)ist[q] * 64;
     }
-    const int n_steps = (D - kb) >> 2;
-    const size_t gstride = (size_t)4 * D;
-    double* my_ring = ring + lane;
+    const int n_pairs = T - t0;
+    double* my_ring = ring + 2 * lane;
     int i_issue = 0, slot_w = 0;
-    auto issue = [&]() {                               // k-step i_issue into ring slot i_issue % depth
-        if (i_issue < n_steps) {
-            double* dst = my_ring + slot_w * (NT * 32);
+    auto issue = [&]() {                               // k-pair i_issue into ring slot i_issue % DEPTH
+        if (i_issue < n_pairs) {
+            double* dst = my_ring + slot_w * (NT * 64);
 #pragma unroll
-            for (int q = 0; q < NT; ++q) {
-                if (i_issue >= ist[q]) cp_async8(dst + q * 32, gp[q]);
-                gp[q] += gstride;
-            }
+            for (int q = 0; q < NT; ++q)
+                if (i_issue >= ist[q]) cp_async16(dst + q * 64, gp[q]);
         }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) gp[q] += 64;
         cp_async_commit();
         ++i_issue;
         slot_w = (slot_w + 1) & (DEPTH - 1);
     };
 #pragma unroll
     for (int i = 0; i < DEPTH - 1; ++i) issue();
-    const XT* ar = rows + (size_t)r8 * S + k4 + kb;
+    const XT* ar = rows + (size_t)r8 * S + k4 + 8 * t0;
     const size_t s8 = (size_t)8 * S;
     int slot_r = 0;
     auto segment = [&](auto na_tag, int i_begin, int i_end) {
         constexpr int NA = decltype(na_tag)::value;
-#pragma unroll 2
         for (int i = i_begin; i < i_end; ++i) {
             issue();
             cp_async_wait<DEPTH - 1>();
-            const double* slot = my_ring + slot_r * (NT * 32);
+            const double* slot = my_ring + slot_r * (NT * 64);
             slot_r = (slot_r + 1) & (DEPTH - 1);
-            double av[MT], bv[NA];
+            double a0[MT], a1[MT];
+            double2 bv[NA];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) av[m] = (double)ar[m * s8];
-            ar += 4;
+            for (int m = 0; m < MT; ++m) {
+                a0[m] = (double)ar[m * s8];
+                a1[m] = (double)ar[m * s8 + 4];
+            }
+            ar += 8;
 #pragma unroll
-            for (int q = 0; q < NA; ++q) bv[q] = slot[q * 32];
+            for (int q = 0; q < NA; ++q) bv[q] = *reinterpret_cast<const double2*>(slot + q * 64);
 #pragma unroll
             for (int q = 0; q < NA; ++q)
 #pragma unroll
-                for (int m = 0; m < MT; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], av[m], bv[q]);
+                for (int m = 0; m < MT; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], a0[m], bv[q].x);
+#pragma unroll
+            for (int q = 0; q < NA; ++q)
+#pragma unroll
+                for (int m = 0; m < MT; ++m) dmma_m8n8k4(acc[m][q][0], acc[m][q][1], a1[m], bv[q].y);
         }
     };
-    // segment s: tiles 0..s active, k-steps [ist[s], ist[s+1])
+    // segment s: tiles 0..s active, k-pairs [ist[s], ist[s+1])
     if constexpr (NT == 2) {
         segment(std::integral_constant<int, 1>{}, 0, ist[1]);
-        segment(std::integral_constant<int, 2>{}, ist[1], n_steps);
+        segment(std::integral_constant<int, 2>{}, ist[1], n_pairs);
     } else {
         segment(std::integral_constant<int, 1>{}, 0, ist[1]);
         segment(std::integral_constant<int, 2>{}, ist[1], ist[2]);
         segment(std::integral_constant<int, 3>{}, ist[2], ist[3]);
-        segment(std::integral_constant<int, 4>{}, ist[3], n_steps);
+        segment(std::integral_constant<int, 4>{}, ist[3], n_pairs);
     }
     cp_async_wait<0>();
 }
@@ -146,7 +165,7 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
     R* th_all = reinterpret_cast<R*>(smem_raw);
     R* xs_all = th_all + (size_t)CH * S;
     R* ring_all = xs_all + (size_t)CH * S;
-    R* red = ring_all + (size_t)kDkWarps * kDkDepth * NT * 32;
+    R* red = ring_all + (size_t)kDkWarps * kDkDepth * NT * 64;
     R* s_inv = red + kDkWarps * CH * 2;
     R* s_c = s_inv + CH;
     R* s_zi = s_c + CH;
@@ -158,7 +177,7 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
     float* s_cdf = s_mean + (size_t)n_stored * D;
     R* th = th_all + (size_t)o * S;
     R* xs = xs_all + (size_t)o * S;
-    R* ring = ring_all + (size_t)warp * kDkDepth * NT * 32;
+    R* ring = ring_all + (size_t)warp * kDkDepth * NT * 64;
 
     const long long c = (long long)blockIdx.x * CH + o;             // chain of this lane group
     const bool valid = c < a.B;
@@ -192,6 +211,9 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
 
     for (int step = 0; step < a.n_steps; ++step) {
         const long long row = (long long)step * a.B + c;
+#ifdef KLHR_DENSE_TIMING
+        const long long tq0 = clock64();
+#endif
         // ---------------------------------------------------------------- A. variates and direction (LPC lanes per chain)
         if (valid) {
             if constexpr (kReplay) {
@@ -256,10 +278,19 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
                 if (j == 0) s_inv[o] = R(1) / r_sqrt(ss);      // rho = x / ||x + tol||  (klhr.py:153)
             }
         }
+#ifdef KLHR_DENSE_TIMING
+        const long long tq1 = clock64();
+#endif
         __syncthreads();
+#ifdef KLHR_DENSE_TIMING
+        const long long tq2 = clock64();
+#endif
         // ---------------------------------------------------------------- B. V = X L on the FP64 tensor cores
         double vf[MT][NT][2];
         dk_tri_product<MT, NT>(xs_all, S, Lm, D, ring, warp, lane, vf);
+#ifdef KLHR_DENSE_TIMING
+        const long long tq3 = clock64();
+#endif
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
             double pa = 0, pb = 0;
@@ -279,7 +310,13 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
                 red[(warp * CH + 8 * m + r8) * 2 + 1] = pb;
             }
         }
+#ifdef KLHR_DENSE_TIMING
+        const long long tq4 = clock64();
+#endif
         __syncthreads();
+#ifdef KLHR_DENSE_TIMING
+        const long long tq5 = clock64();
+#endif
         // ---------------------------------------------------------------- C. fit, proposal, MH (thread per chain)
         if (tid < CH) {
             R cmove = 0;
@@ -322,7 +359,13 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
             }
             s_c[tid] = cmove;
         }
+#ifdef KLHR_DENSE_TIMING
+        const long long tq6 = clock64();
+#endif
         __syncthreads();
+#ifdef KLHR_DENSE_TIMING
+        const long long tq7 = clock64();
+#endif
         // ---------------------------------------------------------------- D. move: theta += c x, w += c V
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -361,6 +404,11 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
         }
         // no barrier: phase A of the next draw writes only this group's own xs row and scalars, which nobody
         // else reads before the barrier that follows it; s_c / red are rewritten two barriers from here
+#ifdef KLHR_DENSE_TIMING
+        if (blockIdx.x == 0 && lane == 0 && step == 40)
+            printf("plain warp %d: A %lld | wait %lld | product %lld | fold %lld | wait %lld | C %lld | wait %lld | D %lld\n", warp, tq1 - tq0,
+                   tq2 - tq1, tq3 - tq2, tq4 - tq3, tq5 - tq4, tq6 - tq5, tq7 - tq6, clock64() - tq7);
+#endif
     }
     if (valid)
         for (int i = j; i < D; i += LPC) g_theta[c * D + i] = th[i];
@@ -381,7 +429,7 @@ __host__ inline size_t densek_smem_bytes(const StepArgs& a, bool replay) {
     const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     size_t b = (size_t)2 * kDkChains * S * 8;                                  // theta, x
-    b += (size_t)kDkWarps * kDkDepth * NT * 32 * 8;                            // cp.async rings
+    b += (size_t)kDkWarps * kDkDepth * NT * 64 * 8;                            // cp.async rings
     b += (size_t)(kDkWarps * kDkChains * 2 + 6 * kDkChains) * 8;               // red, inv, c, z_init, z_prop, log u, u
     b += (size_t)(D + (size_t)n_stored * D + ((n_cols + 3) & ~3)) * 4;         // sd, mean columns, cdf
     return b;

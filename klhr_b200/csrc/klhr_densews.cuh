@@ -7,7 +7,7 @@
 //     memory in the fragment layout's home positions (each thread only ever touches its own 32 entries, and only
 //     between the product and the update), so that the product loop has the registers to keep loads, converts and
 //     DMMAs of neighbouring k-steps in flight;
-//   * 4 PRODUCER warps (4 lanes per chain): under the product on X(t) they apply the move of draw t-1 (theta += c x, theta
+//   * 8 PRODUCER warps (8 lanes per chain): under the product on X(t) they apply the move of draw t-1 (theta += c x, theta
 //     in global memory / L2: nothing else on the device reads it), draw X(t+1) and the scalar variates of draw t+1
 //     (Philox + Box-Muller) into the buffer the move has just released; the first of them also runs the closed-form fit
 //     of draw t (one thread per chain) as soon as the partial sums are in.
@@ -18,8 +18,13 @@
 
 namespace klhr {
 
-constexpr int kWsTensor = 256, kWsProducer = 128, kWsThreads = kWsTensor + kWsProducer;
-constexpr int kWsDepth = 8;                        // k-steps of L in flight per tensor warp
+#ifndef KLHR_WS_PRODUCER_LANES
+#define KLHR_WS_PRODUCER_LANES 8
+#endif
+constexpr int kWsLpc = KLHR_WS_PRODUCER_LANES;     // producer lanes per chain: 4 -> 4 producer warps (168 registers per thread), 8 -> 8 (128)
+constexpr int kWsTensor = 256, kWsProducer = 32 * kWsLpc, kWsThreads = kWsTensor + kWsProducer;
+static_assert(kWsLpc == 4 || kWsLpc == 8, "producer lanes per chain: 4 or 8");
+constexpr int kWsDepth = 4;                        // k-PAIRS (8 rows of L) in flight per tensor warp
 constexpr int kWsBuf = 2;
 
 __device__ __forceinline__ void ws_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
     //   | (floats) xf[2][CH][S] (= one [CH][S] double tile while w is initialised) | sd[D] | mean[n_stored][D] | cdf[n_cols]
     R* w_all = reinterpret_cast<R*>(smem_raw);
     R* ring_all = w_all + (size_t)CH * SW;
-    R* red = ring_all + (size_t)8 * kWsDepth * NT * 32;
+    R* red = ring_all + (size_t)8 * kWsDepth * NT * 64;
     R* s_c = red + 8 * CH * 2;
     R* s_var = s_c + 2 * CH;                           // per buffer: inv, z_init, z_prop, log u, u
     float* xf_all = reinterpret_cast<float*>(s_var + kWsBuf * 5 * CH);
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
         const int r8 = lane >> 2, k4 = lane & 3;
         double wf[MT][NT][2];
         dk_tri_product<MT, NT, double, kWsDepth>(reinterpret_cast<const R*>(xf_all), S, Lm, D,
-                                                 ring_all + (size_t)warp * kWsDepth * NT * 32, warp, lane, wf);
+                                                 ring_all + (size_t)warp * kWsDepth * NT * 64, warp, lane, wf);
 #pragma unroll
         for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -90,23 +95,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
         const int o = tid >> 3, j = tid & 7;
         const int r8 = lane >> 2, k4 = lane & 3;
         const bool valid = chain0 + o < a.B;
-        R* ring = ring_all + (size_t)warp * kWsDepth * NT * 32;
+        R* ring = ring_all + (size_t)warp * kWsDepth * NT * 64;
         for (int step = 0; step < a.n_steps; ++step) {
+#ifdef KLHR_DENSE_TIMING
+            const long long tq0 = clock64();
+#endif
             __syncthreads();                           // X(step) drawn; c(step - 1) applied to w
+#ifdef KLHR_DENSE_TIMING
+            const long long tq1 = clock64();
+#endif
             const int cur = step & 1;
             double vf[MT][NT][2];
             dk_tri_product<MT, NT, float, kWsDepth>(xf_all + (size_t)cur * CH * S, S, Lm, D, ring, warp, lane, vf);
-            double2 wfr[MT][NT];                       // this thread's fragments of w: live from here to the update below only
+#ifdef KLHR_DENSE_TIMING
+            const long long tq2 = clock64();
+#endif
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 double pa = 0, pb = 0;
 #pragma unroll
-                for (int q = 0; q < NT; ++q) {
-                    wfr[m][q] = *reinterpret_cast<const double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4);
+                for (int q = 0; q < NT; ++q) {         // this thread's fragments of w: read here, read-modify-written below
+                    const double2 wq = *reinterpret_cast<const double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4);
                     pa = fma(vf[m][q][0], vf[m][q][0], pa);
-                    pb = fma(wfr[m][q].x, vf[m][q][0], pb);
+                    pb = fma(wq.x, vf[m][q][0], pb);
                     pa = fma(vf[m][q][1], vf[m][q][1], pa);
-                    pb = fma(wfr[m][q].y, vf[m][q][1], pb);
+                    pb = fma(wq.y, vf[m][q][1], pb);
                 }
                 pa += __shfl_xor_sync(0xffffffffu, pa, 1);
                 pa += __shfl_xor_sync(0xffffffffu, pa, 2);
@@ -124,16 +137,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
                 const R inv = s_var[(size_t)cur * 5 * CH + o];
                 for (int i = j; i < D; i += kOct) g[i] = (R)xc[i] * inv;
             }
+#ifdef KLHR_DENSE_TIMING
+            const long long tq3 = clock64();
+#endif
             ws_bar_sync(2, kWsTensor + 32);            // c(step) is known: w += c V
+#ifdef KLHR_DENSE_TIMING
+            if (blockIdx.x == 0 && lane == 0 && step == 40)
+                printf("ws tensor warp %d: wait top %lld | product %lld | fold %lld | wait c %lld\n", warp, tq1 - tq0, tq2 - tq1, tq3 - tq2, clock64() - tq3);
+#endif
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const R cm = s_c[(step & 1) * CH + 8 * m + r8];
 #pragma unroll
                 for (int q = 0; q < NT; ++q) {
-                    double2 t = wfr[m][q];
+                    double2* wp = reinterpret_cast<double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4);
+                    double2 t = *wp;
                     t.x = fma(cm, vf[m][q][0], t.x);
                     t.y = fma(cm, vf[m][q][1], t.y);
-                    *reinterpret_cast<double2*>(w_all + (size_t)(8 * m + r8) * SW + 8 * dk_tile(q, warp) + 2 * k4) = t;
+                    *wp = t;
                 }
             }
         }
@@ -141,9 +162,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
     } else {
         // ============================================================ producer warps
         const int ptid = tid - kWsTensor;
-        const int pc = ptid >> 2, q4 = ptid & 3;       // chain slot, lane of its group of 4
+        constexpr int LPC = kWsLpc;
+        const int pc = ptid / LPC, q4 = ptid % LPC;    // chain slot, lane of its group of LPC
         const bool pvalid = chain0 + pc < a.B;
-        const unsigned gmask = 0xFu << (4 * ((ptid & 31) >> 2));   // the 4 lanes of this chain (validity is uniform over them)
+        const unsigned gmask = (LPC == 8 ? 0xFFu : 0xFu) << (LPC * ((ptid & 31) / LPC));   // the lanes of this chain (validity is uniform over them)
         const unsigned long long cid = (unsigned long long)(a.chain_offset + chain0 + pc);
         const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
         const bool fitter = ptid < 32;                 // the first producer warp also fits: thread ptid <-> chain ptid
@@ -159,7 +181,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
             if (cm == R(0)) return;
             const float2* x2 = reinterpret_cast<const float2*>(xf_all + ((size_t)(step & 1) * CH + pc) * S);
 #pragma unroll 8
-            for (int i = q4; i < D / 2; i += 4) {
+            for (int i = q4; i < D / 2; i += LPC) {
                 double2 t = th2[i];
                 const float2 x = x2[i];
                 t.x = fma(cm, (double)x.x, t.x);
@@ -191,17 +213,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
                     var[3 * CH + pc] = r_log(u);
                 }
             }
-            const R u_col = __shfl_sync(gmask, sv0, 0, 4);
+            const R u_col = __shfl_sync(gmask, sv0, 0, LPC);
             int jcol = 0;
             if (n_cols > 1)                            // searchsorted(cdf, u, 'right'), klhr.py:147
                 while (jcol < n_cols - 1 && (float)u_col >= s_cdf[jcol]) ++jcol;
             const float* mcol = (n_cols && jcol < n_stored) ? s_mean + (size_t)jcol * D : nullptr;
             // block b = 0 .. D / 32 - 1 of lane j8 = 0..7 holds elements 32 b + j8 + 8 r (word r) at slot kSlotDir + j8 + 8 b;
-            // this thread takes j8 = 2 q4 and 2 q4 + 1, all blocks of one j8 advancing round by round together
+            // this thread takes j8 = q4 (8 lanes per chain) or 2 q4, 2 q4 + 1 (4 lanes), all blocks of one j8 advancing
+            // round by round together
             R ss = 0;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const int j8 = 2 * q4 + h;
+            for (int h = 0; h < 8 / LPC; ++h) {
+                const int j8 = (8 / LPC) * q4 + h;
                 uint32_t wv[2 * NT][4];
                 Philox::blockN<2 * NT>(c0, c1, d0, kSlotDir + (uint32_t)j8, 8u, k0s, k1d, wv);
 #pragma unroll
@@ -219,18 +242,28 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
                     }
                 }
             }
-            ss += __shfl_xor_sync(gmask, ss, 1);
-            ss += __shfl_xor_sync(gmask, ss, 2);
+#pragma unroll
+            for (int off = 1; off < LPC; off <<= 1) ss += __shfl_xor_sync(gmask, ss, off);
             if (q4 == 0) var[pc] = R(1) / r_sqrt(ss);  // rho = x / ||x + tol||  (klhr.py:153)
         };
 
         if (a.n_steps > 0) draw_direction(0);
         for (int step = 0; step < a.n_steps; ++step) {
             __syncthreads();
+#ifdef KLHR_DENSE_TIMING
+            const long long pq0 = clock64();
+#endif
             // under the tensor warps' product on X(step): the move of draw step - 1 (its direction sits in the buffer that
             // X(step + 1) is about to overwrite -- same lanes, program order), then X(step + 1)
             if (step > 0) move(step - 1);
+#ifdef KLHR_DENSE_TIMING
+            const long long pq1 = clock64();
+#endif
             if (step + 1 < a.n_steps) draw_direction(step + 1);
+#ifdef KLHR_DENSE_TIMING
+            const long long pq2 = clock64();
+            if (blockIdx.x == 0 && (ptid & 31) == 0 && step == 40) printf("ws producer warp %d: move %lld | direction %lld\n", ptid >> 5, pq1 - pq0, pq2 - pq1);
+#endif
             if (fitter) {
                 ws_bar_sync(1, kWsTensor + 32);        // sums of draw `step`
                 const R* var = s_var + (size_t)(step & 1) * 5 * CH;
@@ -296,7 +329,7 @@ __host__ inline size_t densews_smem_bytes(const StepArgs& a) {
     const int n_cols = a.dir.mean_cols ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     size_t b = (size_t)32 * SW * 8;                                            // w = L' theta
-    b += (size_t)8 * kWsDepth * NT * 32 * 8;                                   // cp.async rings
+    b += (size_t)8 * kWsDepth * NT * 64 * 8;                                   // cp.async rings
     b += (size_t)(8 * 32 * 2 + 2 * 32 + kWsBuf * 5 * 32) * 8;                  // red, c (two draws), variates (two buffers)
     b += (size_t)kWsBuf * 32 * S * 4;                                          // X, two fp32 buffers (= the theta staging tile)
     b += (size_t)(D + (size_t)n_stored * D + ((n_cols + 3) & ~3)) * 4;         // sd, mean columns, cdf

@@ -19,10 +19,10 @@ def test_dense_kernel_is_dispatched_and_replays_the_oracle(N, rho):
     model = kb.BSModel(stan_file="stan/corr-normal.stan", data=data, device=device())
     kfit, _ = fit_pair("gauss")
     info = kb.launch_info(model, kfit, dtype=torch.float64, free_running=True, accumulate=False, device=device())
-    # free-running launches: the warp-specialised kernel (8 tensor + 4 producer warps; w = L'theta fp64, two fp32 direction
+    # free-running launches: the warp-specialised kernel (8 tensor + 8 producer warps; w = L'theta fp64, two fp32 direction
     # buffers, per-warp cp.async rings); replay below runs on dense_kernel, sample() rows too
-    want_smem = 32 * (N + 8) * 8 + 8 * 8 * (N // 64) * 32 * 8 + (8 * 32 * 2 + 2 * 32 + 2 * 5 * 32) * 8 + 2 * 32 * (N + 4) * 4 + N * 4
-    assert info["threads"] == 384 and info["ctas_per_sm"] == 1 and info["smem"] == want_smem
+    want_smem = 32 * (N + 8) * 8 + 8 * 4 * (N // 64) * 64 * 8 + (8 * 32 * 2 + 2 * 32 + 2 * 5 * 32) * 8 + 2 * 32 * (N + 4) * 4 + N * 4
+    assert info["threads"] == 512 and info["ctas_per_sm"] == 1 and info["smem"] == want_smem
     rng = np.random.default_rng(N)
     for B in (1, 77, 1000):                                   # ragged last CTA (32 chains per CTA)
         theta = rng.normal(size=(B, N)) * 0.7

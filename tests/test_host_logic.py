@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.klhr_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.klhr_abi_version() == _lib.ABI_VERSION == 4
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.klhr_model_eval(None, 0, None, None, None, 0, None) < 0
     assert "model is NULL" in _lib.last_error()
