@@ -194,3 +194,29 @@ def test_argument_validation_of_every_entry_point_without_a_gpu():
     assert lib.klhr_run(m, f, None, 0, None, 8, 0, 0, 5, 1, C.byref(pooled_only_s1), None, None) < 0
     assert lib.klhr_outer_scratch_doubles(0, 10) == 0 and lib.klhr_outer_scratch_doubles(1000, 10) > 0
     del acc
+
+
+def test_corr_pack_cholesky_layout_and_errors():
+    """klhr_corr_pack_cholesky (host helper of the C ABI, no device needed): the packed stream holds, for column tile
+    nt, k-pair p >= nt and lane (r8, k4), the B-fragment values L[8p + k4][8nt + r8] and L[8p + 4 + k4][8nt + r8]."""
+    import ctypes as C
+    from klhr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for D in (128, 256):
+        T = D // 8
+        L = np.tril(rng.normal(size=(D, D)))
+        n = lib.klhr_corr_pack_cholesky(None, D, None)
+        assert n == 64 * T * (T + 1) // 2
+        out = np.full(n, np.nan)
+        assert lib.klhr_corr_pack_cholesky(L.ctypes.data, D, out.ctypes.data) == n
+        off = lambda nt: 64 * (nt * T - nt * (nt - 1) // 2)
+        for nt, p, lane in ((0, 0, 0), (0, T - 1, 31), (3, 3, 5), (T - 1, T - 1, 17), (7, T - 2, 30)):
+            r8, k4 = lane >> 2, lane & 3
+            base = off(nt) + ((p - nt) * 32 + lane) * 2
+            assert out[base] == L[8 * p + k4, 8 * nt + r8] and out[base + 1] == L[8 * p + 4 + k4, 8 * nt + r8]
+        assert not np.isnan(out).any()
+        # every entry of the lower triangle's tiles appears exactly once
+        assert np.isclose(np.sort(out[out != 0]), np.sort(L[L != 0])).all()
+    assert lib.klhr_corr_pack_cholesky(None, 100, None) < 0 and "128 or 256" in _lib.last_error()
+    assert lib.klhr_corr_pack_cholesky(None, 128, np.empty(1).ctypes.data) < 0
