@@ -230,22 +230,26 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
             } else {
                 const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
                 const uint32_t d0 = (uint32_t)draw, k1d = k1s ^ (uint32_t)(draw >> 32);
-                // scalar variates (slots 0..2, same mapping as chain_scalars): lanes 0..2 expand one slot each
+                // scalar variates (slots 0..2, same mapping and arithmetic as chain_scalars): lanes 0..2 expand one slot
+                // each.  Lanes 1 and 2 both need the logarithm of the 53-bit uniform in (w0, w1): ONE convergent call --
+                // as divergent branches these long dependent fp64 chains would run one after the other (a quarter of
+                // this phase); only lane 1's square root and cosine remain on their own
                 R sv0 = 0;
                 if (j < 3) {
                     uint32_t wv[4];
                     Philox::block(c0, c1, d0, (uint32_t)j, k0s, k1d, wv);
+                    const R u53 = u01_53(wv[0], wv[1]);
+                    const R lg = r_log(u53);
+                    float z0, z1;
+                    box_muller_f32(wv[2], wv[3], z0, z1);
                     if (j == 0) {
-                        float z0, z1;
-                        box_muller_f32(wv[2], wv[3], z0, z1);
                         sv0 = (R)u01_32(wv[0]);
                         s_zi[o] = (R)z0;
                     } else if (j == 1) {
-                        s_zp[o] = box_muller_f64(u01_53(wv[0], wv[1]), u01_53(wv[2], wv[3]));
+                        s_zp[o] = sqrt(-2.0 * lg) * cospi(2.0 * u01_53(wv[2], wv[3]));     // = box_muller_f64
                     } else {
-                        const R u = u01_53(wv[0], wv[1]);
-                        s_u[o] = u;
-                        s_lu[o] = r_log(u);                    // log of the accept uniform, off the critical path of the fit
+                        s_u[o] = u53;
+                        s_lu[o] = lg;                          // log of the accept uniform, off the critical path of the fit
                     }
                 }
                 const R u_col = __shfl_sync(0xffffffffu, sv0, 0, LPC);

@@ -197,20 +197,21 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
             const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
             const uint32_t d0 = (uint32_t)draw, k1d = k1s ^ (uint32_t)(draw >> 32);
             R sv0 = 0;
-            if (q4 < 3) {                              // slots 0..2, same mapping as chain_scalars
-                uint32_t wv[4];
+            if (q4 < 3) {                              // slots 0..2, same mapping and arithmetic as chain_scalars; the logarithm
+                uint32_t wv[4];                        // lanes 1 and 2 both need is ONE convergent call (see dense_kernel)
                 Philox::block(c0, c1, d0, (uint32_t)q4, k0s, k1d, wv);
+                const R u53 = u01_53(wv[0], wv[1]);
+                const R lg = r_log(u53);
+                float z0, z1;
+                box_muller_f32(wv[2], wv[3], z0, z1);
                 if (q4 == 0) {
-                    float z0, z1;
-                    box_muller_f32(wv[2], wv[3], z0, z1);
                     sv0 = (R)u01_32(wv[0]);
                     var[1 * CH + pc] = (R)z0;
                 } else if (q4 == 1) {
-                    var[2 * CH + pc] = box_muller_f64(u01_53(wv[0], wv[1]), u01_53(wv[2], wv[3]));
+                    var[2 * CH + pc] = sqrt(-2.0 * lg) * cospi(2.0 * u01_53(wv[2], wv[3]));     // = box_muller_f64
                 } else {
-                    const R u = u01_53(wv[0], wv[1]);
-                    var[4 * CH + pc] = u;
-                    var[3 * CH + pc] = r_log(u);
+                    var[4 * CH + pc] = u53;
+                    var[3 * CH + pc] = lg;
                 }
             }
             const R u_col = __shfl_sync(gmask, sv0, 0, LPC);
