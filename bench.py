@@ -524,8 +524,8 @@ def run_b200(args):
         cfg_lines["c4"] = run_config(
             "c4", "stan/corr-normal D=256 dense precision (Sigma_ij = 0.9^|i-j|), KLHR Gaussian line fit, 16384 chains/GPU, fp64",
             lambda: kb.KLHR(cm, seed=SEED, chains=16_384, warmup=1000, device=dev), 100,
-            2 * 256 * 8 + 16, peaks["fp64_dmma_tflops"], "peaks.fp64_dmma_tflops", "klhr::dense_kernel (csrc/klhr_densek.cuh, DMMA)",
-            "V = L' rho (P = L L') for the 32 chains of a CTA on mma.sync.m8n8k4.f64, w = L' theta carried in registers: the "
+            2 * 256 * 8 + 16, peaks["fp64_dmma_tflops"], "peaks.fp64_dmma_tflops", "klhr::dense_ws_kernel (csrc/klhr_densews.cuh + klhr_densek.cuh, DMMA)",
+            "V = L' rho (P = L L') for the 32 chains of a CTA on mma.sync.m8n8k4.f64 (8 tensor warps), w = L' theta carried along, directions / fit / move on 8 producer warps: the "
             "triangular product executes ~D^2 flops per chain-draw where P rho needs 2 D^2 = 131 kflop (SURVEY 8d, `algorithmic_*`)",
             alg_flops=2 * 256 * 256)
         ak = kb.BSModel(stan_file="stan/arK.stan", data={"K": 5, "T": 10_000, "y": ark_series().tolist()}, device=dev)
