@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip configs c3..c5)")
-    ap.add_argument("--profile-region", default="", choices=["", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--profile-region", default="", choices=["", "c2", "c3", "c3_dims11", "c4", "c5"],
                     help="cudaProfilerStart/Stop around the first timed launch of that config (ncu --profile-from-start off)")
     ap.add_argument("--ref-draws-per-step", type=int, default=400)
     ap.add_argument("--ref-procs", type=int, default=0, help="0 = all host cores")
@@ -520,6 +520,13 @@ def run_b200(args):
             2 * 2 * 8 + 16, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", "klhr::chain_kernel (csrc/klhr_chain.cuh)",
             "thread-per-chain 4-parameter Newton fit on the O(1) line restriction; bound by fp64 arithmetic incl. exp/log",
         )
+        fm11 = kb.BSModel(stan_file="stan/funnel.stan", data={"D": 10}, device=dev)
+        cfg_lines["c3_dims11"] = run_config(
+            "c3_dims11", "stan/funnel dims=11 (the 10-D funnel of write_experiments.py:127), KLHRSINH sinh-arcsinh line fit, overrelaxed=False, "
+                         "262144 chains/GPU, fp64",
+            lambda: kb.KLHRSINH(fm11, seed=SEED, chains=262_144, warmup=1000, overrelaxed=False, device=dev), 20,
+            2 * 11 * 8 + 16, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", "klhr::chain_kernel (csrc/klhr_chain.cuh)",
+            "as c3; the elementwise gradient clip walks the 11 components only when its bound trips")
         cm = kb.BSModel(stan_file="stan/corr-normal.stan", data={"N": 256, "rho": 0.9}, device=dev)
         cfg_lines["c4"] = run_config(
             "c4", "stan/corr-normal D=256 dense precision (Sigma_ij = 0.9^|i-j|), KLHR Gaussian line fit, 16384 chains/GPU, fp64",
