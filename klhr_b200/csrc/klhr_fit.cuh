@@ -275,11 +275,9 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
     const R invd = R(1) / q.d;
     R f = 0, g1 = 0, g2 = 0, g3 = 0, g0 = 0;
     R h00 = 0, h01 = 0, h02 = 0, h03 = 0, h11 = 0, h12 = 0, h13 = 0, h22 = 0, h23 = 0, h33 = 0;
-#ifndef KLHR_KL_UNROLL
-#define KLHR_KL_UNROLL 1
-#endif
-    constexpr int kUnroll = G == 1 ? KLHR_KL_UNROLL : 1;
-#pragma unroll(kUnroll)
+    // not unrolled on purpose: two nodes in flight cost more in registers (spills at the 128-register budget of the chain
+    // kernel, fewer resident warps above it) than their overlap returns (measured)
+#pragma unroll 1
     for (int n = lane; n < fp.N; n += G) {
         const R w = (R)fp.w[n];
         const R a = ((R)fp.cx[n] + q.e) * invd;
