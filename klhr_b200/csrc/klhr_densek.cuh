@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kDkThreads, 32 / kDkChains) dense_kernel(const
         const long long tq0 = clock64();
 #endif
         // ---------------------------------------------------------------- A. variates and direction (LPC lanes per chain)
+        __syncwarp();                                          // the move below read x elements that other lanes of the group redraw here
         if (valid) {
             if constexpr (kReplay) {
                 const R* g_rho = reinterpret_cast<const R*>(a.rho);

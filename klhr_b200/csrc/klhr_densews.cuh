@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) dense_ws_kernel(const __grid_co
             // under the tensor warps' product on X(step): the move of draw step - 1 (its direction sits in the buffer that
             // X(step + 1) is about to overwrite -- same lanes, program order), then X(step + 1)
             if (step > 0) move(step - 1);
+            __syncwarp();                              // a lane's move reads elements that another lane of its chain redraws below
 #ifdef KLHR_DENSE_TIMING
             const long long pq1 = clock64();
 #endif
