@@ -168,9 +168,14 @@ class ClockSampler:
         self.proc = None
         self.rows = None
         try:
+            import shutil
+            exe = shutil.which("nvidia-smi") or "nvidia-smi"
+            # full path + close_fds=False: CPython then starts the child with posix_spawn instead of fork -- a fork()
+            # makes every later multi-threaded LAPACK call of this process hang when the bench runs under ncu
+            # (tools/dev/t_ncu.py reproduces it)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
-                 "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                [exe, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL, close_fds=False)
             import atexit
             atexit.register(self._kill)                  # never leave the sampler behind if the bench dies
         except OSError:
@@ -260,6 +265,13 @@ def run_b200(args):
     rb = 8 if dtype == torch.float64 else 4
     launches = [0]                                   # klhr_run launches inside timed regions (gpu_launches)
 
+    trace_on = bool(os.environ.get("KLHR_BENCH_TRACE"))
+    t_start = time.time()
+
+    def trace(msg):                                  # progress on stderr (KLHR_BENCH_TRACE=1): where a run under a profiler spends its time
+        if trace_on and rank == 0:
+            print(f"[bench +{time.time() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -299,8 +311,9 @@ def run_b200(args):
         `cold_phase_s`); the second is the phase itself (`phase_s`), like every other timed region after warm-up."""
         out = []
         sampler = None
-        for _ in range(2):
+        for k_pass in range(2):
             del sampler
+            trace(f"adaptation pass {k_pass}")
             sampler = make_sampler()
             barrier()
             torch.cuda.synchronize()
@@ -313,6 +326,7 @@ def run_b200(args):
     def timed_steps(sampler, draws, k, w, do_flush, tag=""):
         """k launches of `draws` draws, each bracketed by CUDA events on the launching stream; max over ranks of
         the summed device time.  Returns (total_ms, wall window)."""
+        trace(f"timed steps {tag or '-'}: {w} warm-up + {k} x {draws} draws")
         for _ in range(w):
             sampler.run(draws)
         torch.cuda.synchronize()
@@ -496,9 +510,11 @@ def run_b200(args):
             a_draws = world * smp.chains * 1000
             t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, 2, False, tag)
             val = world * smp.chains * draws * Kc / (t_ms * 1e-3)
+            trace(f"{tag}: timed steps done")
             ev0 = int(smp._evals_total.item())
             smp.run(draws)
             evals = (int(smp._evals_total.item()) - ev0) / (smp.chains * draws)
+            trace(f"{tag}: evaluation count done")
             out = {"workload": workload, "value": val, "unit": UNIT, "ms_per_step": t_ms / Kc, "steps": Kc,
                    "draws_per_step": draws, "chains_per_gpu": smp.chains, "acceptance": smp.acceptance_probability,
                    "line_evaluations_per_draw": evals,
@@ -527,7 +543,9 @@ def run_b200(args):
             lambda: kb.KLHRSINH(fm11, seed=SEED, chains=262_144, warmup=1000, overrelaxed=False, device=dev), 20,
             2 * 11 * 8 + 16, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", "klhr::chain_kernel (csrc/klhr_chain.cuh)",
             "as c3; the elementwise gradient clip walks the 11 components only when its bound trips")
+        trace("c4: building the model (precision, Cholesky factor, packing)")
         cm = kb.BSModel(stan_file="stan/corr-normal.stan", data={"N": 256, "rho": 0.9}, device=dev)
+        trace("c4: model built")
         cfg_lines["c4"] = run_config(
             "c4", "stan/corr-normal D=256 dense precision (Sigma_ij = 0.9^|i-j|), KLHR Gaussian line fit, 16384 chains/GPU, fp64",
             lambda: kb.KLHR(cm, seed=SEED, chains=16_384, warmup=1000, device=dev), 100,
