@@ -508,7 +508,7 @@ def run_b200(args):
                        alg_flops=None):
             smp, a_s, a_cold = adapt_phase(make_sampler, 1000)
             a_draws = world * smp.chains * 1000
-            t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, 2, False, tag)
+            t_ms, (c0_, c1_) = timed_steps(smp, draws, Kc, max(W, 3), False, tag)
             val = world * smp.chains * draws * Kc / (t_ms * 1e-3)
             trace(f"{tag}: timed steps done")
             ev0 = int(smp._evals_total.item())
