@@ -284,9 +284,10 @@ __device__ void kl_sinh(const typename Model::Coef& cf, const R (&eta)[4], const
         const R ac = r_clamp(a, -c, c);
         // sinh, cosh, tanh and log cosh from ONE exponential (|ac| <= scale_clip = 300 keeps e^ac
         // finite in fp64); absolute accuracy ~1 ulp of cosh, which is what T and the KL sums need
-        // e^-ac by a second exponential (independent of the first: the two overlap) instead of a division, and
-        // tanh through a Newton reciprocal of cosh (1 <= cosh <= e^300 / 2: no special cases to guard)
-        const R E = r_exp(ac), Ei = r_exp(-ac);
+        // e^-ac and tanh through Newton reciprocals of e^ac and cosh (e^-300 <= e^ac <= e^300, 1 <= cosh <= e^300 / 2: no
+        // special cases to guard) instead of IEEE divisions (~25 dependent instructions each); a second exponential for
+        // e^-ac overlaps with the first but costs 35 more instructions per node: measured 6 % slower
+        const R E = r_exp(ac), Ei = r_rcp_normal(E);
         const R sh = R(0.5) * (E - Ei), ch = R(0.5) * (E + Ei);
         const R th = sh * r_rcp_normal(ch);
         const R sech2 = R(1) - th * th;
