@@ -364,7 +364,8 @@ template <int G, typename R, typename Model, int n>
 __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const FitParams& fp, int lane,
                               unsigned m, int& nev, bool& converged, R& s_out, const ClipCtx<R>& cc) {
     const unsigned wm = __activemask();        // the lanes that entered together stay in lock-step
-    KLState<R, n> S;
+    R S_f = 0, S_s = 1;        // objective and family scale at the last accepted point (its gradient and Hessian are used up
+                               // in the trip that accepts it: nothing else of the 22-double KLState has to be carried)
     R p[n], trial[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) { trial[i] = eta[i]; p[i] = 0; }
@@ -385,20 +386,21 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
                 accepted = true;
                 have_S = true;
             } else {
-                const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S.f));
+                const R slack = R(8) * Num<R>::eps * (R(1) + r_abs(S_f));
                 accepted = r_finite(St.f) &&
-                           ((St.f <= S.f + (R)fp.c1 * t * gp + slack) || !r_finite(S.f) || in_basin);
+                           ((St.f <= S_f + (R)fp.c1 * t * gp + slack) || !r_finite(S_f) || in_basin);
             }
             if (accepted) {
 #pragma unroll
                 for (int i = 0; i < n; ++i) eta[i] = trial[i];
-                S = St;
+                S_f = St.f;
+                S_s = St.s;
                 R gmax = 0;
                 bool gnan = false;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    gmax = r_max(gmax, r_abs(S.g[i]));
-                    gnan = gnan || (S.g[i] != S.g[i]);
+                    gmax = r_max(gmax, r_abs(St.g[i]));
+                    gnan = gnan || (St.g[i] != St.g[i]);
                 }
                 // flat valley: inside the basin a Newton step must at least halve the gradient; two in
                 // a row that do not -> stop (see oracle/batched.py:stage2_newton)
@@ -411,12 +413,12 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
                     done = true;                   // Newton-step budget exhausted, or flat valley
                 } else {
                     g_prev = gmax;
-                    newton_direction<R, n>(S, fp, p);
+                    newton_direction<R, n>(St, fp, p);
                     gp = 0;
 #pragma unroll
-                    for (int i = 0; i < n; ++i) gp += S.g[i] * p[i];
+                    for (int i = 0; i < n; ++i) gp += St.g[i] * p[i];
                     if (!r_finite(gp)) gp = 0;
-                    s_cur = scale_of<R, n>(eta, fp);
+                    s_cur = St.s;                  // = scale_of(eta): the evaluation formed it with the same operations
                     in_basin = !gnan && gmax <= (R)fp.basin;
                     t = 1;
                     bt = 0;
@@ -435,7 +437,7 @@ __device__ void stage2_newton(const typename Model::Coef& cf, R (&eta)[n], const
         }
     }
     converged = conv;
-    s_out = S.s;               // scale at the returned eta (the last accepted evaluation)
+    s_out = S_s;               // scale at the returned eta (the last accepted evaluation)
 }
 
 // ------------------------------------------------------------------ family densities / transport
