@@ -232,6 +232,16 @@ __device__ __forceinline__ void box_muller_f32(uint32_t a, uint32_t b, float& z0
     z1 = rad * __sinf(ang);
 }
 
+// z0 of box_muller_f32 alone (same operations, same bits), where the sine branch has no coordinate to go to
+__device__ __forceinline__ float box_muller_f32_cos(uint32_t a, uint32_t b) {
+    const float u = u01_32(a);
+    float lg, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg));
+    const float ang = (float)b * 1.4629180792671596e-09f;
+    return rad * __cosf(ang);
+}
+
 // One fp64 normal from two 53-bit uniforms (the proposal variate): only the cosine branch is ever used
 __device__ __forceinline__ double box_muller_f64(double u, double v) {
     return sqrt(-2.0 * log_c(u)) * cospi(2.0 * v);

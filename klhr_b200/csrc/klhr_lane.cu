@@ -14,11 +14,22 @@ static int lane_g() {
     return g;
 }
 
+// KLHR_LANE_TAIL=0 in the environment keeps the last, single-quad trip inside the trip loop (measurements)
+static bool lane_tail_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("KLHR_LANE_TAIL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 int launch_lane(const StepArgs& a, cudaStream_t st, LaunchInfo* info) {
     const bool scaled = a.mp.id == KLHR_MODEL_ILL_NORMAL;
     if (lane_g() == 1)
-        return scaled ? launch_lane_typed<true, 1>(a, st, info) : launch_lane_typed<false, 1>(a, st, info);
-    return scaled ? launch_lane_typed<true, 2>(a, st, info) : launch_lane_typed<false, 2>(a, st, info);
+        return scaled ? launch_lane_typed<true, 1, false>(a, st, info) : launch_lane_typed<false, 1, false>(a, st, info);
+    if (lane_split_tail(a.mp.D) && lane_tail_enabled())
+        return scaled ? launch_lane_typed<true, 2, true>(a, st, info) : launch_lane_typed<false, 2, true>(a, st, info);
+    return scaled ? launch_lane_typed<true, 2, false>(a, st, info) : launch_lane_typed<false, 2, false>(a, st, info);
 }
 
 }  // namespace klhr

@@ -87,8 +87,9 @@ __host__ __device__ __forceinline__ int lane_n_trips(int D) {
     return 2 * (D >> 5) + (rem > 4 ? 2 : (rem > 0 ? 1 : 0));
 }
 
-template <bool kScaled, int G, bool kDraws>
+template <bool kScaled, int G, bool kDraws, bool kTail>
 __global__ void __launch_bounds__(kWarp * G, KLHR_LANE_MINCTAS) lane_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!kTail || G == 2, "the split tail is the two-lanes-per-chain form");
     using R = double;
     using Model = DiagNormal<R, kScaled>;
     constexpr int NC = kWarp / G;                             // chains per warp
@@ -155,7 +156,11 @@ __global__ void __launch_bounds__(kWarp * G, KLHR_LANE_MINCTAS) lane_kernel(cons
     unsigned long long n_evals = 0;
     double2* my_th = th2 + cl;
     float4* my_x = x4 + cl;
-    const int n_trips = lane_n_trips(D);
+    // kTail (D mod 32 in 1..4, see lane_split_tail): the last trip would hold ONE coordinate quad -- 16 normals drawn
+    // for <= 4 coordinates, on one lane of the chain while the other idles (D = 100: a quarter of the sweep's
+    // instructions for 4 % of its coordinates).  That quad is taken out of the trip loop and split between the two
+    // lanes of the chain (tail_* below); the loop then runs full trips only, the same number on both lanes.
+    const int n_trips = lane_n_trips(D) - (kTail ? 1 : 0);
     const bool traced = a.tr.eta || a.tr.zp || a.tr.r || a.tr.accept || a.tr.evals || a.tr.rho || a.tr.z_init;
 
     // cooperative copy of the warp's states to global rows dst[c][0..D) (thinned draws, final write-back)
@@ -195,6 +200,19 @@ __global__ void __launch_bounds__(kWarp * G, KLHR_LANE_MINCTAS) lane_kernel(cons
         philox_trip(s2, t2, w_mid);
         advance();
     }
+    // split tail: lane part p owns coordinates e_tail + 2 p, e_tail + 2 p + 1 = word 0 of the Philox blocks at slots
+    // kSlotDir + 8 (D / 32) + 2 p (+ 1) -- the same (slot, word) -> element map as everywhere else (kSlotDir)
+    const int q_tail = (D & ~31) >> 2;
+    float zt0 = 0.f, zt1 = 0.f;                               // the two tail normals of the NEXT draw to sweep
+    auto tail_normals = [&](int step) {
+        const unsigned long long draw = (unsigned long long)(a.draw_offset + step);
+        uint32_t wt[2][4];
+        Philox::blockN<2>(c0, c1, (uint32_t)draw, kSlotDir + (uint32_t)(8 * (D >> 5) + 2 * p), 1u, k0,
+                          k1 ^ (uint32_t)(draw >> 32), wt);
+        zt0 = box_muller_f32_cos(wt[0][0], wt[0][1]);
+        zt1 = box_muller_f32_cos(wt[1][0], wt[1][1]);
+    };
+    if constexpr (kTail) tail_normals(0);
 
     // per-draw scalar variates: lane part p draws them for draw step + p once every G draws (they depend on
     // nothing but the counters), the G lanes of a chain then read them from one another -- each chain-draw
@@ -288,8 +306,34 @@ __global__ void __launch_bounds__(kWarp * G, KLHR_LANE_MINCTAS) lane_kernel(cons
         };
 #pragma unroll 1
         for (int t = p; t < n_trips; t += G) {
-            if (32 * (t >> 1) + 4 * (t & 1) + 27 < D) trip(std::true_type{}, t);
+            if (kTail || 32 * (t >> 1) + 4 * (t & 1) + 27 < D) trip(std::true_type{}, t);
             else trip(std::false_type{}, t);
+        }
+        if constexpr (kTail) {
+            // padded coordinates (>= D) carry weight, scale, mean, theta and x = 0: they add exact zeros
+            double2 tt = my_th[(size_t)(2 * q_tail + p) * kPitch];
+            float2* xp = reinterpret_cast<float2*>(&my_x[(size_t)q_tail * NC]) + p;
+            const float2 xo = *xp;
+            const double2 wt2 = s_w2[2 * q_tail + p];
+            const float2 sd = reinterpret_cast<const float2*>(&s_sd4[q_tail])[p];
+            const float2 mn = reinterpret_cast<const float2*>(&mcol[q_tail])[p];
+            float2 xn;
+            xn.x = fmaf(sd.x, zt0, mn.x);
+            xn.y = fmaf(sd.y, zt1, mn.y);
+            tt.x = fma(cp, (double)xo.x, tt.x);               // pending move of the previous draw
+            tt.y = fma(cp, (double)xo.y, tt.y);
+            {
+                const R x = (double)xn.x, xw = kScaled ? x * wt2.x : x;
+                sx0 += xn.x;
+                ss0 = fma(x, x, ss0); if (kScaled) sA0 = fma(x, xw, sA0); sB0 = fma(tt.x, xw, sB0);
+            }
+            {
+                const R x = (double)xn.y, xw = kScaled ? x * wt2.y : x;
+                sx1 += xn.y;
+                ss1 = fma(x, x, ss1); if (kScaled) sA1 = fma(x, xw, sA1); sB1 = fma(tt.y, xw, sB1);
+            }
+            my_th[(size_t)(2 * q_tail + p) * kPitch] = tt;
+            *xp = xn;
         }
         __syncwarp();
         if constexpr (kDraws) {
@@ -301,6 +345,8 @@ __global__ void __launch_bounds__(kWarp * G, KLHR_LANE_MINCTAS) lane_kernel(cons
             }
         }
         // ------------------------------------------------------------------ fit, proposal, MH (every lane of the chain)
+        if constexpr (kTail) tail_normals(step + 1);          // integer work that depends on nothing: it fills the
+                                                              // issue slots under the fit's dependent FP64 chain
         R ss = ss0 + ss1, sA = sA0 + sA1, sB = sB0 + sB1;
         float sx = sx0 + sx1;
 #pragma unroll
@@ -388,11 +434,15 @@ __host__ inline size_t lane_smem_bytes(const StepArgs& a, int G = KLHR_LANE_G) {
     return b;
 }
 
-template <bool kScaled, int G>
+// dimensions whose last trip is a single coordinate quad (see kTail in lane_kernel)
+__host__ __device__ __forceinline__ bool lane_split_tail(int D) { return (D & 31) >= 1 && (D & 31) <= 4; }
+
+template <bool kScaled, int G, bool kTail>
 int launch_lane_typed(const StepArgs& a, cudaStream_t st, LaunchInfo* info) {
     const size_t smem = lane_smem_bytes(a, G);
     if (smem > 227 * 1024) return -20;
-    const void* fn = a.acc.draws ? (const void*)lane_kernel<kScaled, G, true> : (const void*)lane_kernel<kScaled, G, false>;
+    const void* fn = a.acc.draws ? (const void*)lane_kernel<kScaled, G, true, kTail>
+                                 : (const void*)lane_kernel<kScaled, G, false, kTail>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -6,7 +6,7 @@ import torch
 
 import klhr_b200 as kb
 from conftest import load_tape
-from gpu_util import device, fit_pair, up
+from gpu_util import DIAG_MODELS, device, fit_pair, up
 from klhr_b200.diagnostics import chain_summary
 from oracle import batched, stan_models
 
@@ -521,6 +521,51 @@ def test_device_exp_log_accuracy():
     with np.errstate(all="ignore"):
         r = np.log(spl)
     assert np.array_equal(np.isnan(g), np.isnan(r)) and np.array_equal(g[~np.isnan(r)], r[~np.isnan(r)])
+
+
+@pytest.mark.parametrize("D", [1, 2, 4, 33, 36, 97, 100, 101, 132])
+def test_lane_kernel_split_tail_dimensions(D):
+    """D mod 32 in 1..4: the lane kernel takes the last coordinate quad out of its trip loop and splits it between
+    the two lanes of a chain (csrc/klhr_lane.cuh, kTail; D = 101 is the first dimension past that case).  Same streams,
+    same chains as the tile and octet kernels up to round-off, over several draws, ragged batches, an adapted
+    direction law, and bitwise independent of where the launches are cut (the tail normals of the next draw are
+    drawn one draw ahead)."""
+    B, S, seed = 777, 7, 5
+    rng = np.random.default_rng(D)
+    theta0 = rng.normal(size=(B, D)) * 0.3
+    cols = np.zeros((2, D))
+    cols[0, 0], cols[1, D - 1] = 1.5, -0.7
+    direction = kb.Direction(mean_cols=up(cols), sd=up(np.linspace(0.5, 2.0, D)), cdf=up(np.array([0.3, 0.8, 1.0])),
+                             n_zero_cols=1)
+    for name in DIAG_MODELS:
+        model = kb.BSModel(stan_file=f"stan/{name}.stan", data={"D": D}, device=device())
+        kfit, ofit = fit_pair("gauss")
+        info = kb.launch_info(model, kfit)
+        assert info["threads"] == 64                               # the two-lane lane kernel is what runs
+        acc_a = torch.zeros(B, dtype=torch.int64, device=device())
+        a = up(theta0)
+        tr = kb.Trace(S, B, D, 2, torch.float64, device(), variates=True, rho=True)
+        kb.run(model, kfit, a, S, seed, direction, accept_count=acc_a, trace=tr)
+        for force in ("tile", "octet"):
+            kfit.force_tile, kfit.force_octet = force == "tile", force == "octet"
+            acc_b = torch.zeros(B, dtype=torch.int64, device=device())
+            b = up(theta0)
+            kb.run(model, kfit, b, S, seed, direction, accept_count=acc_b)
+            torch.cuda.synchronize()
+            assert torch.allclose(a, b, rtol=1e-9, atol=1e-9)
+            assert torch.equal(acc_a, acc_b)
+        kfit.force_tile = kfit.force_octet = False
+        c = up(theta0)
+        kb.run(model, kfit, c, 3, seed, direction, draw_offset=0)
+        kb.run(model, kfit, c, S - 3, seed, direction, draw_offset=3)
+        torch.cuda.synchronize()
+        assert torch.equal(a, c)
+        # the first draw against the oracle on the variates and the direction the kernel emitted
+        g = lambda t: t[0].double().cpu().numpy()
+        ref = batched.step(stan_models.make_model(name, {"D": D}), theta0, g(tr.rho), g(tr.z_init), g(tr.z_prop),
+                           g(tr.u), ofit)
+        assert np.allclose(g(tr.eta), ref["eta"], rtol=1e-10, atol=1e-10)
+        assert np.array_equal(tr.accept[0].cpu().numpy().astype(bool), ref["accept"])
 
 
 @pytest.mark.parametrize("force_tile", [False, True])
