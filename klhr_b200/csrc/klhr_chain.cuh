@@ -11,10 +11,17 @@
 //             the lock-step state machine for 32 chains at once.
 // For the non-Gaussian targets (funnel, rosenbrock, arK) and the sinh-arcsinh family the step is
 // dominated by the fit, which is why this shape wins over the octet kernel there.
+// Small D (<= kChainSerialMaxD: funnel 2 / 11, rosenbrock 4, earnings 4, arK 7): an octet has more lanes than a
+// row has elements, and 8 passes of octet reductions cost more than the rows are worth -- the D-phase is then
+// thread-per-chain too (a.serial_d): every lane stages its own theta row, draws its own direction (the same
+// (slot, word) -> element map, so the same streams) and reduces it with Model::setup<1>, no shuffles.
 #pragma once
+#include <cstdlib>
 #include "klhr_tile.cuh"
 
 namespace klhr {
+
+constexpr int kChainSerialMaxD = 16;
 
 #ifndef KLHR_CHAIN_MINCTAS
 #define KLHR_CHAIN_MINCTAS 16   // 128 registers: the extra resident warps beat the small spills (measured, funnel)
@@ -33,10 +40,13 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
     const int n_cols = (!kReplay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     // shared memory: th_s[4][Dp] | rho[32][Dp] | sd[D] | mean[n_stored][D] | cdf[n_cols]   (all R)
+    // serial D-phase: th[32][Do] | rho[32][Do] | ...  with rows owned by lanes and an ODD pitch Do (conflict-free)
+    const bool serial = a.serial_d != 0;
+    const int Do = D | 1;
     R* th_all = reinterpret_cast<R*>(smem_raw);
     R* th_s = th_all + (size_t)o * Dp;
-    R* rho_all = th_all + (size_t)4 * Dp;
-    R* s_sd = rho_all + (size_t)32 * Dp;
+    R* rho_all = th_all + (serial ? (size_t)32 * Do : (size_t)4 * Dp);
+    R* s_sd = rho_all + (serial ? (size_t)32 * Do : (size_t)32 * Dp);
     R* s_mean = s_sd + D;
     R* s_cdf = s_mean + (size_t)n_stored * D;
 
@@ -99,6 +109,72 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
         const long long g_prev = a.acc.thin_offset + step;
         const bool emit_rt = kDraws && step > 0 && g_prev % a.acc.thin == 0;
         // -------------------------------------------------------------------- D-phase
+        if (serial) {
+            R* th_row = th_all + (size_t)L * Do;
+            R* rh = rho_all + (size_t)L * Do;
+            const R cp = c_pend;
+            if (own_valid && !(last && cp == R(0) && !emit_rt)) {
+                R* row = g_theta + c_own * D;
+                R* drow = nullptr;
+                if constexpr (kDraws)
+                    if (emit_rt) drow = reinterpret_cast<R*>(a.acc.draws) + ((g_prev / a.acc.thin - 1) * a.B + c_own) * D;
+                // theta row -> shared, with the pending move of the previous draw applied
+                for (int i = 0; i < D; ++i) {
+                    R t0 = row[i];
+                    if (cp != R(0)) {
+                        t0 = t0 + cp * rh[i];
+                        row[i] = t0;
+                    }
+                    th_row[i] = t0;
+                    if constexpr (kDraws)
+                        if (drow) drow[i] = t0;
+                }
+            }
+            if (!last && own_valid) {
+                if constexpr (kReplay) {
+                    const R* g_rho = reinterpret_cast<const R*>(a.rho);
+                    for (int i = 0; i < D; ++i) rh[i] = g_rho[c_own * D + i];
+                } else {
+                    const unsigned long long cid = (unsigned long long)(a.chain_offset + c_own);
+                    const uint32_t c0 = (uint32_t)cid, c1 = (uint32_t)(cid >> 32);
+                    const R* mcol = jcol < n_stored ? s_mean + (size_t)jcol * D : nullptr;
+                    R ss = 0;
+                    // element i = b + 8 r  <->  Philox slot kSlotDir + b, word r (D <= 16: r = 0, 1 = the two
+                    // normals of the block's first Box-Muller pair)
+                    for (int b0 = 0; b0 < D && b0 < 8; b0 += 4) {
+                        uint32_t w[4][4];
+                        Philox::blockN<4>(c0, c1, d0, kSlotDir + (uint32_t)b0, 1u, k0, k1d, w);
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) {
+                            const int i = b0 + bb;
+                            if (i < D) {
+                                float z0, z1 = 0.0f;
+                                if (i + 8 < D) box_muller_f32(w[bb][0], w[bb][1], z0, z1);
+                                else z0 = box_muller_f32_cos(w[bb][0], w[bb][1]);
+                                const R x = (R)fmaf((float)s_sd[i], z0, mcol ? (float)mcol[i] : 0.0f);
+                                rh[i] = x;
+                                const R xt = x + tol;
+                                ss += xt * xt;
+                                if (i + 8 < D) {
+                                    const R x1 = (R)fmaf((float)s_sd[i + 8], z1, mcol ? (float)mcol[i + 8] : 0.0f);
+                                    rh[i + 8] = x1;
+                                    const R xt1 = x1 + tol;
+                                    ss += xt1 * xt1;
+                                }
+                            }
+                        }
+                    }
+                    const R inv = R(1) / r_sqrt(ss);      // rho = x / ||x + tol||  (klhr.py:153)
+                    for (int i = 0; i < D; ++i) rh[i] *= inv;
+                }
+                if (a.tr.rho) {
+                    R* g = reinterpret_cast<R*>(a.tr.rho) + ((long long)step * a.B + c_own) * D;
+                    for (int i = 0; i < D; ++i) g[i] = rh[i];
+                }
+                my_cf = Model::template setup<1>(th_row, rh, 0, 0u, a.mp);
+            }
+            __syncwarp();
+        } else
 #pragma unroll 1
         for (int p = 0; p < kPasses; ++p) {
             const int cs = 4 * p + o;
@@ -187,7 +263,8 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
             }
             // sinh family: elementwise gradient clip of klhr_sinh.py:158-161 (theta row: global memory, already
             // carrying the previous draw's move; rho row: this chain's slot of the warp tile)
-            const ClipCtx<R> cc = clip_ctx<R>(a.fp, a.mp, D, g_theta + c_own * D, rho_all + (size_t)(4 * j + o) * Dp);
+            const ClipCtx<R> cc = clip_ctx<R>(a.fp, a.mp, D, g_theta + c_own * D,
+                                              serial ? rho_all + (size_t)L * Do : rho_all + (size_t)(4 * j + o) * Dp);
             fit_and_propose<1, R, Model, NE>(my_cf, a.fp, 0, 0u, z_init, init2, init3, z_prop, u, so, oc, cc);
             if (!kReplay && oc.K > 0 && a.tr.or_r) {
                 a.tr.or_r[(long long)step * a.B + c_own] = oc.r;
@@ -230,17 +307,25 @@ __global__ void __launch_bounds__(kWarp, KLHR_CHAIN_MINCTAS) chain_kernel(const 
     }
 }
 
+// thread-per-chain D-phase for small D; KLHR_CHAIN_SERIAL=0 in the environment keeps the octet D-phase (measurements)
+inline bool chain_serial_d(int D) {
+    static const bool on = [] { const char* e = std::getenv("KLHR_CHAIN_SERIAL"); return !(e && e[0] == '0'); }();
+    return on && D <= kChainSerialMaxD;
+}
+
 inline size_t chain_smem_bytes(const StepArgs& a, int real_bytes, bool replay) {
     const int n_cols = (!replay && a.dir.mean_cols) ? a.dir.n_cols : 0;
     const int n_stored = n_cols ? n_cols - a.dir.n_zero_cols : 0;
     const int Dp = pad_dim(a.mp.D, real_bytes);
-    return ((size_t)36 * Dp + (size_t)(1 + n_stored) * a.mp.D + n_cols) * real_bytes;
+    const size_t rows = chain_serial_d(a.mp.D) ? (size_t)64 * (a.mp.D | 1) : (size_t)36 * Dp;
+    return (rows + (size_t)(1 + n_stored) * a.mp.D + n_cols) * real_bytes;
 }
 
 template <typename R, typename Model>
 int launch_chain_typed(const StepArgs& args_in, int family, bool replay, cudaStream_t st, LaunchInfo* info) {
     StepArgs a = args_in;
     a.Dpad = pad_dim(a.mp.D, (int)sizeof(R));
+    a.serial_d = chain_serial_d(a.mp.D) ? 1 : 0;
     const size_t smem = chain_smem_bytes(a, (int)sizeof(R), replay);
     if (smem > 227 * 1024) return -20;
     const void* fn;

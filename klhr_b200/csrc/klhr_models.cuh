@@ -1,9 +1,10 @@
 // klhr_b200 -- target densities as hand-written device functions (replaces BridgeStan).
 //
 // Each model provides
-//   setup(th, rh, lane, mask, mp) -> Coef   octet-cooperative reductions over the D-vector
-//                                           (th = theta row, rh = rho row, both in shared
-//                                           memory), result uniform across the 8 lanes;
+//   setup<GS>(th, rh, lane, mask, mp) -> Coef   reductions over the D-vector by the GS lanes of a chain: GS = 8
+//                                           octet-cooperative (th = theta row, rh = rho row, both in shared
+//                                           memory), result uniform across the 8 lanes; GS = 1 one thread
+//                                           (lane = 0), no shuffles -- the chain kernel's D-phase for small D;
 //   eval(coef, y) -> Jet                    O(1): l(y) - l(0), l'(y), l''(y) of the line
 //                                           restriction l(y) = lp(theta + y rho);
 //   lp_grad(th, g, lane, mask, mp) -> lp    full-D log density and gradient (the
@@ -58,16 +59,17 @@ struct DiagNormal {
     __device__ static __forceinline__ R wgt(int i, const ModelParams& mp) {
         return kScaled ? __ldg(reinterpret_cast<const R*>(mp.p0) + i) : R(1);
     }
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         R a = 0, b = 0;
-        for (int i = lane; i < mp.D; i += kOct) {
+        for (int i = lane; i < mp.D; i += GS) {
             const R r = rh[i], t = th[i], w = wgt(i, mp);
             a += r * r * w;
             b -= r * t * w;
         }
         Coef c;
-        c.A = oct_sum(a, m);
-        c.Bq = oct_sum(b, m);
+        c.A = grp_sum<GS>(a, m);
+        c.Bq = grp_sum<GS>(b, m);
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
@@ -90,19 +92,20 @@ struct CorrNormal {
     using Self = CorrNormal<R>;
     static constexpr bool kDenseCta = true;     // fp64: CTA-cooperative DMMA path, klhr_dense.cuh
     using Coef = QuadCoef<R>;
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const R* P = reinterpret_cast<const R*>(mp.p0);
         const int D = mp.D;
         R a = 0, b = 0;
-        for (int i = lane; i < D; i += kOct) {
+        for (int i = lane; i < D; i += GS) {
             R v = 0;                                      // v_i = (P rho)_i ; P symmetric -> column walk is coalesced
             for (int k = 0; k < D; ++k) v += __ldg(P + (size_t)k * D + i) * rh[k];
             a += rh[i] * v;
             b -= th[i] * v;
         }
         Coef c;
-        c.A = oct_sum(a, m);
-        c.Bq = oct_sum(b, m);
+        c.A = grp_sum<GS>(a, m);
+        c.Bq = grp_sum<GS>(b, m);
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
@@ -128,10 +131,11 @@ struct AR1 {
     using Self = AR1<R>;
     static constexpr bool kDenseCta = false;
     using Coef = QuadCoef<R>;
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const R al = (R)mp.s0, ib2 = (R)mp.s1;
         R a = 0, b = 0;
-        for (int i = lane; i < mp.D; i += kOct) {
+        for (int i = lane; i < mp.D; i += GS) {
             if (i == 0) {
                 a += rh[0] * rh[0];
                 b -= rh[0] * th[0];
@@ -143,8 +147,8 @@ struct AR1 {
             }
         }
         Coef c;
-        c.A = oct_sum(a, m);
-        c.Bq = oct_sum(b, m);
+        c.A = grp_sum<GS>(a, m);
+        c.Bq = grp_sum<GS>(b, m);
         return c;
     }
     __device__ static __forceinline__ Jet<R> eval(const Coef& c, R y) { return quad_eval(c, y); }
@@ -177,18 +181,19 @@ struct Funnel {
     using Self = Funnel<R>;
     static constexpr bool kDenseCta = false;
     struct Coef { R x0, r0, a0, a1, a2, hd, l0, t1, r1; };     // t1, r1: first alpha and its direction (dims = 2 clip path)
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         R a0 = 0, a1 = 0, a2 = 0;
-        for (int i = 1 + lane; i < mp.D; i += kOct) {
+        for (int i = 1 + lane; i < mp.D; i += GS) {
             const R t = th[i], r = rh[i];
             a0 += t * t;
             a1 += t * r;
             a2 += r * r;
         }
         Coef c;
-        c.a0 = oct_sum(a0, m);
-        c.a1 = oct_sum(a1, m);
-        c.a2 = oct_sum(a2, m);
+        c.a0 = grp_sum<GS>(a0, m);
+        c.a1 = grp_sum<GS>(a1, m);
+        c.a2 = grp_sum<GS>(a2, m);
         c.x0 = th[0];
         c.r0 = rh[0];
         c.hd = R(0.5) * (R)mp.i0;
@@ -274,10 +279,11 @@ struct Rosenbrock {
     using Self = Rosenbrock<R>;
     static constexpr bool kDenseCta = false;
     struct Coef { R b1, b2, b3, b4; };      // l(y) - l(0) = b1 y + b2 y^2 + b3 y^3 + b4 y^4
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const int Dh = mp.i0;
         R p1 = 0, p2 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
-        for (int i = lane; i < Dh; i += kOct) {
+        for (int i = lane; i < Dh; i += GS) {
             const R v = th[i], t = th[Dh + i], rv = rh[i], rt = rh[Dh + i];
             const R c0 = t - v * v, c1 = rt - R(2) * v * rv, c2 = -rv * rv;
             p1 += (v - R(1)) * rv;
@@ -287,8 +293,8 @@ struct Rosenbrock {
             q3 += c1 * c2;
             q4 += c2 * c2;
         }
-        p1 = oct_sum(p1, m); p2 = oct_sum(p2, m);
-        q1 = oct_sum(q1, m); q2 = oct_sum(q2, m); q3 = oct_sum(q3, m); q4 = oct_sum(q4, m);
+        p1 = grp_sum<GS>(p1, m); p2 = grp_sum<GS>(p2, m);
+        q1 = grp_sum<GS>(q1, m); q2 = grp_sum<GS>(q2, m); q3 = grp_sum<GS>(q3, m); q4 = grp_sum<GS>(q4, m);
         Coef c;
         c.b1 = -p1 - R(100) * q1;
         c.b2 = -R(0.5) * p2 - R(50) * q2;
@@ -371,9 +377,10 @@ struct ARK {
         return -R(0.5) * (c.p0 + y * (R(2) * c.p1 + y * c.p2)) - R(0.5) * r_exp(R(2) * u) - c.nm1 * u
                - R(0.5) * r_exp(-R(2) * u) * (c.q0 + y * (R(2) * c.q1 + y * c.q2));
     }
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         Coef c;
-        gram_forms(th, rh, lane, m, mp, c.q0, c.q1, c.q2, c.p0, c.p1, c.p2, nullptr);
+        gram_forms<GS>(th, rh, lane, m, mp, c.q0, c.q1, c.q2, c.p0, c.p1, c.p2, nullptr);
         c.u0 = th[mp.D - 1];
         c.ru = rh[mp.D - 1];
         c.nm1 = (R)(mp.i1 - 1);                 // (T-K) u - u  (likelihood minus Jacobian)
@@ -439,6 +446,7 @@ struct Earnings {
                - R(0.5) * r_exp(-R(2) * us) * S;
     }
     // D = 4: every lane computes the same coefficients, no reductions needed
+    template <int GS = kOct>
     __device__ static Coef setup(const R* th, const R* rh, int lane, unsigned m, const ModelParams& mp) {
         const Stats s = stats(mp);
         Coef c;

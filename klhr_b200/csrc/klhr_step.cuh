@@ -33,6 +33,7 @@ struct StepArgs {
     void* theta;
     long long B;
     int Dpad;
+    int serial_d;      // chain kernel: thread-per-chain D-phase (small D), set by its launcher
     // replay inputs
     const void* rho;
     const void* z_init;
@@ -388,6 +389,7 @@ struct KlArgs {
     void* hess;          // [B][NE][NE] or null
     long long B;
     int Dpad;
+    int serial_d;      // chain kernel: thread-per-chain D-phase (small D), set by its launcher
 };
 
 template <typename R, typename Model, int NE>

@@ -609,6 +609,45 @@ def test_chain_kernel_thinned_draws_match_octet_kernel(model_name, data, cls):
         assert torch.allclose(out_a[-1], c.theta, rtol=1e-12, atol=1e-12)
 
 
+def test_chain_kernel_thread_per_chain_d_phase_draws_the_octet_kernels_directions():
+    """Small D (<= 16): the chain kernel's D-phase is thread-per-chain (csrc/klhr_chain.cuh, a.serial_d) -- same
+    (slot, word) -> element map as the octet reductions it replaces, so the directions of the first draw agree with
+    the octet kernel's to rounding (the norm is summed in another order), for every small target, with an adapted
+    direction law and a ragged batch; later draws agree chain by chain wherever no fit ended on its budget."""
+    rng = np.random.default_rng(2)
+    y = stan_models.simulate_ark_series(T=300, seed=5)
+    cases = [("funnel", {"D": 1}, "sinh"), ("funnel", {"D": 10}, "sinh"), ("funnel", {"D": 15}, "gauss"),
+             ("rosenbrock", {"D": 2}, "gauss"), ("arK", {"K": 5, "T": 300, "y": y.tolist()}, "gauss"),
+             ("earnings", {"N": 50, "earn": (3 + rng.normal(size=50)).tolist(),
+                           "height": (66 + 4 * rng.normal(size=50)).tolist()}, "gauss"),
+             ("normal", {"D": 3}, "sinh")]
+    B, S, seed = 333, 4, 21
+    for name, data, family in cases:
+        model = kb.BSModel(stan_file=f"stan/{name}.stan", data=data, device=device())
+        D = model.dim()
+        theta0 = rng.normal(size=(B, D)) * 0.3
+        cols = np.zeros((2, D))
+        cols[0, 0], cols[1, D - 1] = 1.5, -0.7
+        direction = kb.Direction(mean_cols=up(cols), sd=up(np.linspace(0.5, 2.0, D)),
+                                 cdf=up(np.array([0.3, 0.8, 1.0])), n_zero_cols=1)
+        out = {}
+        for force_octet in (False, True):
+            kfit, _ = fit_pair(family)
+            kfit.force_octet = force_octet
+            th = up(theta0)
+            tr = kb.Trace(S, B, D, kfit.n_eta, torch.float64, device(), variates=True, rho=True)
+            acc = torch.zeros(B, dtype=torch.int64, device=device())
+            kb.run(model, kfit, th, S, seed, direction, chain_offset=(1 << 33) + 1, accept_count=acc, trace=tr)
+            torch.cuda.synchronize()
+            out[force_octet] = (th, tr, acc)
+        (th_c, tr_c, acc_c), (th_o, tr_o, acc_o) = out[False], out[True]
+        assert torch.allclose(tr_c.rho[0], tr_o.rho[0], rtol=0, atol=1e-14), name
+        assert torch.equal(tr_c.z_init[0], tr_o.z_init[0]) and torch.equal(tr_c.u[0], tr_o.u[0])
+        same = torch.isclose(th_c, th_o, rtol=1e-8, atol=1e-8).all(dim=1)
+        assert float(same.double().mean()) >= 0.97, (name, float(same.double().mean()))
+        assert float((acc_c == acc_o).double().mean()) >= 0.97, name
+
+
 def test_adaptation_variants_scale_dir_cov_and_method_two():
     """The constructor switches of the direction law (klhr.py:143-153,202-210): ``scale_dir_cov`` divides the
     window variances by the variances of the model gradient, ``eigen_method_one=False`` uses one mean vector
