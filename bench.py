@@ -484,10 +484,7 @@ def run_b200(args):
 
     kernel_name = ("klhr::lane_kernel (csrc/klhr_lane.cuh)" if info["threads"] in (32, 64) and info["smem"] > 30000 else
                    "klhr::tile_kernel (csrc/klhr_tile.cuh)" if info["threads"] == 32 else "klhr::step_kernel (csrc/klhr_step.cuh)")
-    # normals generated per chain-draw: 16 per trip of the lane kernel's sweep; a last trip of one coordinate quad
-    # (D mod 32 in 1..4) is split between the chain's two lanes instead and draws only its 4 cosine-branch normals
-    # (4 Philox blocks for them: csrc/klhr_lane.cuh, kTail)
-    n_gen = 32 * (D // 32) + (4 if 1 <= D % 32 <= 4 else (32 if D % 32 > 4 else 0))
+    n_gen = lane_normals_generated(D)
     roof = fp64_roofline(
         "c2", value / world, (2 * D * rb + 16) / S, peaks["fp64_fma_tflops"], "peaks.fp64_fma_tflops", kernel_name,
         f"S = {S} draws are fused per launch with theta resident in shared memory: HBM sees one read and one write of "
@@ -617,6 +614,14 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def lane_normals_generated(D):
+    """Direction normals the lane kernel draws per chain-draw (csrc/klhr_lane.cuh): 16 per trip of its sweep (4 Philox
+    blocks; trip t covers the 4 coordinate quads at 32 (t // 2) + 4 (t % 2) + 8 r); a last trip of ONE quad (D mod 32 in
+    1..4, kTail) is split between the chain's two lanes instead and draws only the 4 cosine-branch normals it needs."""
+    rem = D % 32
+    return 32 * (D // 32) + (4 if 1 <= rem <= 4 else (32 if rem > 4 else 0))
 
 
 def main():

@@ -33,3 +33,22 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                          text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_normals_accounting_follows_the_lane_kernels_element_map():
+    """`roofline.normals.generated_per_chain_draw` against a walk of the lane kernel's sweep (csrc/klhr_lane.cuh): trip t
+    covers the coordinate quads at e = 32 (t // 2) + 4 (t % 2) + 8 r, r = 0..3, and draws 16 normals whatever part of it
+    lies below D; a last trip of a single quad is split between the chain's two lanes and draws 4 (kTail)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    for D in range(1, 300):
+        trips = [t for t in range(2 * (D // 32 + 1)) if 32 * (t // 2) + 4 * (t % 2) < D]
+        rem = D % 32
+        tail = 1 <= rem <= 4
+        assert len(trips) == 2 * (D // 32) + (2 if rem > 4 else (1 if rem else 0))
+        if tail:
+            last = trips.pop()
+            quads = [r for r in range(4) if 32 * (last // 2) + 4 * (last % 2) + 8 * r < D]
+            assert quads == [0]                                    # one quad: coordinates D - rem .. D - 1
+        assert bench.lane_normals_generated(D) == 16 * len(trips) + (4 if tail else 0)
+        assert bench.lane_normals_generated(D) >= D
